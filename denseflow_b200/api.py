@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference's algorithm-object interface for the hot path.
+
+The reference (C++) creates `cuda::OpticalFlowDual_TVL1::create()` / `cuda::FarnebackOpticalFlow::create()`
+(/root/reference/src/denseflow_gpu.cpp:299,301) and calls `alg->calc(gray_a, gray_b, flow, stream)` (:327,:329)
+inside `DenseFlow::calc_optflows_imp` (:282-370).  The classes here keep those names, argument meaning and
+error behaviour (unknown algorithm / unsupported size -> RuntimeError with the reference's message) on top of
+the C ABI (include/denseflow_b200.h).  Everything numeric happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DenseOpticalFlow:
+    """cv::cuda::DenseOpticalFlow look-alike bound to one GPU."""
+
+    algorithm = None
+
+    def __init__(self, algorithm, device=0, max_width=1920, max_height=1080, variant="default"):
+        self._L = _lib.load(variant)
+        self._h = C.c_void_p()
+        self.algorithm = algorithm
+        self.device = device
+        rc = self._L.dfb_create(algorithm.encode(), device, max_width, max_height, C.byref(self._h))
+        if rc != _lib.DFB_OK:
+            msg = self._L.dfb_last_error(None).decode()
+            self._h = None
+            raise RuntimeError(msg)  # reference: std::runtime_error -> what() + exit 1 (tools/denseflow.cpp:93-96)
+
+    # -- lifetime (Ptr<>::release, src/denseflow_gpu.cpp:345-355) --
+    def release(self):
+        if getattr(self, "_h", None):
+            self._L.dfb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _lib.DFB_OK:
+            raise RuntimeError(self._L.dfb_last_error(self._h).decode() or "dfb error %d" % rc)
+
+    def set(self, name, value):
+        self._check(self._L.dfb_set_param(self._h, name.encode(), float(value)))
+        return self
+
+    def get(self, name):
+        v = C.c_double()
+        self._check(self._L.dfb_get_param(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    # -- calc(I0, I1) -> flow (CV_32FC2), src/denseflow_gpu.cpp:327/:329 --
+    def calc(self, a, b, flow=None, stream=None):
+        """a, b: uint8 [H,W] numpy arrays (host path: upload, calc, download) or CUDA torch tensors
+        (device path: enqueued on `stream` / torch's current stream, asynchronous)."""
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, np.uint8)
+            b = np.ascontiguousarray(b, np.uint8)
+            if a.ndim != 2 or a.shape != b.shape:
+                raise RuntimeError("calc: frames must be two CV_8UC1 images of the same size")
+            h, w = a.shape
+            if flow is None:
+                flow = np.empty((h, w, 2), np.float32)
+            self._check(self._L.dfb_calc_host(self._h, a.ctypes.data, b.ctypes.data, w, h, flow.ctypes.data))
+            return flow
+        import torch
+        if a.dtype != torch.uint8 or a.dim() != 2 or a.shape != b.shape or not a.is_cuda:
+            raise RuntimeError("calc: frames must be two CV_8UC1 CUDA tensors of the same size")
+        h, w = a.shape
+        if flow is None:
+            flow = torch.empty((h, w, 2), dtype=torch.float32, device=a.device)
+        s = stream if stream is not None else torch.cuda.current_stream(a.device).cuda_stream
+        self._check(self._L.dfb_calc_device(self._h, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), w, h,
+                                            flow.data_ptr(), flow.stride(0) * 4, C.c_void_p(s)))
+        return flow
+
+    # -- the batch shape of calc_optflows_imp (src/denseflow_gpu.cpp:307-342) --
+    def calc_batch(self, frames, step=1, flows=None, bound=None):
+        """frames: sequence of uint8 [H,W] host arrays (or one [N,H,W] array).  Returns M = max(N-|step|,0)
+        flows [M,H,W,2] float32, or with bound=B the quantised (qx, qy) uint8 [M,H,W] planes
+        (convertFlowToImage, src/common.cpp:4-16, done on the GPU)."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        n = len(frames)
+        if n == 0:
+            return np.empty((0, 0, 0, 2), np.float32)
+        h, w = frames[0].shape
+        m = max(n - abs(step), 0)
+        fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        if bound is None:
+            if flows is None:
+                flows = np.empty((m, h, w, 2), np.float32)
+            op = (C.c_void_p * max(m, 1))(*[flows[i].ctypes.data for i in range(m)])
+            self._check(self._L.dfb_calc_batch_host(self._h, fp, n, step, w, h, op))
+            return flows
+        qx = np.empty((m, h, w), np.uint8)
+        qy = np.empty((m, h, w), np.uint8)
+        xp = (C.c_void_p * max(m, 1))(*[qx[i].ctypes.data for i in range(m)])
+        yp = (C.c_void_p * max(m, 1))(*[qy[i].ctypes.data for i in range(m)])
+        self._check(self._L.dfb_calc_batch_host_u8(self._h, fp, n, step, w, h, int(bound), xp, yp))
+        return qx, qy
+
+    def calc_batch_device(self, frames, step=1, flows=None, stream=None):
+        """frames: CUDA uint8 tensor [N,H,W] (contiguous); flows: CUDA float32 [M,H,W,2]."""
+        import torch
+        n, h, w = frames.shape
+        m = max(n - abs(step), 0)
+        if flows is None:
+            flows = torch.empty((m, h, w, 2), dtype=torch.float32, device=frames.device)
+        s = stream if stream is not None else torch.cuda.current_stream(frames.device).cuda_stream
+        self._check(self._L.dfb_calc_batch_device(self._h, frames.data_ptr(), n, step, w, h, flows.data_ptr(),
+                                                  C.c_void_p(s)))
+        return flows
+
+    def quantise_device(self, flow, bound):
+        import torch
+        h, w = flow.shape[:2]
+        qx = torch.empty((h, w), dtype=torch.uint8, device=flow.device)
+        qy = torch.empty((h, w), dtype=torch.uint8, device=flow.device)
+        s = torch.cuda.current_stream(flow.device).cuda_stream
+        self._check(self._L.dfb_quantise_device(self._h, flow.data_ptr(), flow.stride(0) * 4, w, h, int(bound),
+                                                qx.data_ptr(), qy.data_ptr(), w, C.c_void_p(s)))
+        return qx, qy
+
+    # -- counters for the roofline arithmetic --
+    def tvl1_stats(self):
+        st = _lib.Tvl1Stats()
+        self._check(self._L.dfb_get_tvl1_stats(self._h, C.byref(st)))
+        iters = np.array(st.iters[:], np.int64).reshape(16, 16)[:st.nscales, :st.warps] if st.warps else None
+        # rows of the C array are indexed s*warps + w
+        flat = np.array(st.iters[:], np.int64)
+        iters = flat[:st.nscales * st.warps].reshape(st.nscales, st.warps)
+        sizes = [(st.level_w[i], st.level_h[i]) for i in range(st.nscales)]
+        return iters, sizes
+
+    def counters(self):
+        c = _lib.Counters()
+        self._check(self._L.dfb_get_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in c._fields_}
+
+    def reset_counters(self):
+        self._check(self._L.dfb_reset_counters(self._h))
+
+
+class OpticalFlowDual_TVL1(DenseOpticalFlow):
+    @classmethod
+    def create(cls, device=0, max_width=1920, max_height=1080, variant="default"):
+        """cuda::OpticalFlowDual_TVL1::create() with upstream defaults (src/denseflow_gpu.cpp:299)."""
+        return cls("tvl1", device, max_width, max_height, variant)
+
+
+class FarnebackOpticalFlow(DenseOpticalFlow):
+    @classmethod
+    def create(cls, device=0, max_width=1920, max_height=1080, variant="default"):
+        """cuda::FarnebackOpticalFlow::create() with upstream defaults (src/denseflow_gpu.cpp:301)."""
+        return cls("farn", device, max_width, max_height, variant)
+
+
+def create(algorithm, device=0, max_width=1920, max_height=1080, variant="default"):
+    """The algorithm switch of calc_optflows_imp (src/denseflow_gpu.cpp:291-304, error text of :296 / :336)."""
+    if algorithm == "tvl1":
+        return OpticalFlowDual_TVL1.create(device, max_width, max_height, variant)
+    if algorithm == "farn":
+        return FarnebackOpticalFlow.create(device, max_width, max_height, variant)
+    return DenseOpticalFlow(algorithm, device, max_width, max_height, variant)  # raises with the reference's message
+
+
+def convert_flow_to_image(flow, bound):
+    """Not provided on the host: the quantiser runs on the GPU (calc_batch(bound=...) / quantise_device)."""
+    raise NotImplementedError("use calc_batch(..., bound=B) or DenseOpticalFlow.quantise_device")

@@ -1,0 +1,419 @@
+// dfb_api.cu — the extern "C" boundary declared in include/denseflow_b200.h.
+// Replaces the statements of the per-pair loop of DenseFlow::calc_optflows_imp
+// (/root/reference/src/denseflow_gpu.cpp:313-342): upload x2 (:317-318), calc (:327/:329),
+// download (:339) — plus the batch shape of the whole function (:307-342).
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "tvl1.cuh"
+
+using namespace dfb;
+
+struct dfb_handle {
+    int device = 0;
+    int max_w = 0, max_h = 0;
+    std::string algorithm;
+    std::unique_ptr<FlowAlgorithm> alg;
+    std::string last_error;
+    dfb_counters counters{};
+
+    // host-path plumbing: three streams so H2D of frame i+1, compute of pair i and D2H of flow i-1 overlap
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    static constexpr int kFrameRing = 4;  // device u8 frames (dead as soon as their pyramid is built)
+    static constexpr int kFlowRing = 3;   // device flow / quantised outputs
+    uint8_t *d_frame[kFrameRing] = {};
+    size_t d_frame_pitch = 0;
+    float *d_flow[kFlowRing] = {};
+    uint8_t *d_qx[kFlowRing] = {}, *d_qy[kFlowRing] = {};
+    cudaEvent_t ev_in[kFrameRing] = {}, ev_pyr[kFrameRing] = {}, ev_done[kFlowRing] = {}, ev_out[kFlowRing] = {};
+    // pinned staging for pageable caller buffers
+    uint8_t *h_frame[kFrameRing] = {};
+    float *h_flow[kFlowRing] = {};
+    uint8_t *h_q[kFlowRing] = {};
+};
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+int fail(dfb_handle *h, int code, const std::string &msg) {
+    if (h)
+        h->last_error = msg;
+    else {
+        std::lock_guard<std::mutex> lk(g_err_mutex);
+        g_create_error = msg;
+    }
+    return code;
+}
+
+template <typename F> int guarded(dfb_handle *h, F &&f) {
+    try {
+        return f();
+    } catch (const CudaError &e) {
+        return fail(h, DFB_ERR_CUDA, e.what());
+    } catch (const std::exception &e) {
+        return fail(h, DFB_ERR_INVALID_ARG, e.what());
+    } catch (...) {
+        return fail(h, DFB_ERR_INVALID_ARG, "unknown exception");
+    }
+}
+
+bool is_pinned_or_device(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int check_size(dfb_handle *h, int w, int h_) {
+    if (w <= 0 || h_ <= 0) return fail(h, DFB_ERR_INVALID_ARG, "width/height must be positive");
+    if (w > h->max_w || h_ > h->max_h)
+        return fail(h, DFB_ERR_SIZE, "frame " + std::to_string(w) + "x" + std::to_string(h_) + " exceeds the " +
+                                         std::to_string(h->max_w) + "x" + std::to_string(h->max_h) + " given to dfb_create");
+    return DFB_OK;
+}
+
+void ensure_host_path(dfb_handle *h) {
+    if (h->s_in) return;
+    DFB_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    DFB_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    DFB_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    const size_t fpitch = (size_t)round_up(h->max_w, 128);
+    h->d_frame_pitch = fpitch;
+    for (int i = 0; i < dfb_handle::kFrameRing; ++i) {
+        DFB_CUDA(cudaMalloc(&h->d_frame[i], fpitch * h->max_h));
+        DFB_CUDA(cudaHostAlloc(&h->h_frame[i], (size_t)h->max_w * h->max_h, cudaHostAllocDefault));
+        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < dfb_handle::kFlowRing; ++i) {
+        DFB_CUDA(cudaMalloc(&h->d_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float)));
+        DFB_CUDA(cudaMalloc(&h->d_qx[i], (size_t)h->max_w * h->max_h));
+        DFB_CUDA(cudaMalloc(&h->d_qy[i], (size_t)h->max_w * h->max_h));
+        DFB_CUDA(cudaHostAlloc(&h->h_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float), cudaHostAllocDefault));
+        DFB_CUDA(cudaHostAlloc(&h->h_q[i], (size_t)h->max_w * h->max_h * 2, cudaHostAllocDefault));
+        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+}
+
+// The batch shape of calc_optflows_imp (src/denseflow_gpu.cpp:307-342) over host buffers.
+// quantise: bound > 0 => emit two u8 planes per pair instead of the float2 field.
+int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int step, int w, int hh, float *const *flows,
+               int bound, uint8_t *const *qx, uint8_t *const *qy) {
+    if (int rc = check_size(h, w, hh)) return rc;
+    if (n_frames < 0 || !frames) return fail(h, DFB_ERR_INVALID_ARG, "frames is null");
+    if (step == 0) return fail(h, DFB_ERR_INVALID_ARG, "step must be non-zero for flow extraction");
+    const int astep = std::abs(step);
+    const int M = std::max(n_frames - astep, 0);  // :308
+    if (M == 0) return DFB_OK;
+    ensure_host_path(h);
+    FlowAlgorithm &alg = *h->alg;
+    alg.ensure_slots(astep + 2);
+    const int nslots = alg.num_slots();
+    const size_t fbytes = (size_t)w * hh;
+    constexpr int FR = dfb_handle::kFrameRing, OR = dfb_handle::kFlowRing;
+
+    int uploaded = 0;  // frames [0, uploaded) have H2D + pyramid enqueued
+    auto upload_until = [&](int last) {
+        for (; uploaded <= last; ++uploaded) {
+            const int f = uploaded, r = f % FR;
+            if (f >= FR) DFB_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_pyr[r], 0));  // ring slot's pyramid is built
+            const uint8_t *src = frames[f];
+            if (!is_pinned_or_device(src)) {
+                // the pinned staging buffer of this ring slot is free once its previous H2D finished
+                if (f >= FR) DFB_CUDA(cudaEventSynchronize(h->ev_in[r]));
+                std::memcpy(h->h_frame[r], src, fbytes);
+                src = h->h_frame[r];
+            }
+            DFB_CUDA(cudaMemcpy2DAsync(h->d_frame[r], h->d_frame_pitch, src, w, w, hh, cudaMemcpyHostToDevice, h->s_in));
+            DFB_CUDA(cudaEventRecord(h->ev_in[r], h->s_in));
+            h->counters.h2d_bytes += fbytes;
+            DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_in[r], 0));
+            alg.prepare_frame(h->d_frame[r], h->d_frame_pitch, w, hh, f % nslots, h->s_compute);
+            DFB_CUDA(cudaEventRecord(h->ev_pyr[r], h->s_compute));
+        }
+    };
+
+    std::vector<int> pending_copy(OR, -1);  // pair index whose staged output still has to be memcpy'd out
+    auto drain = [&](int ring) {
+        const int j = pending_copy[ring];
+        if (j < 0) return;
+        DFB_CUDA(cudaEventSynchronize(h->ev_out[ring]));
+        if (bound > 0) {
+            std::memcpy(qx[j], h->h_q[ring], fbytes);
+            std::memcpy(qy[j], h->h_q[ring] + fbytes, fbytes);
+        } else {
+            std::memcpy(flows[j], h->h_flow[ring], fbytes * 2 * sizeof(float));
+        }
+        pending_copy[ring] = -1;
+    };
+
+    for (int j = 0; j < M; ++j) {
+        const int a = step > 0 ? j : j + astep;  // :315
+        const int b = step > 0 ? j + astep : j;  // :316
+        upload_until(std::min(std::max(a, b) + 1, n_frames - 1));  // one frame ahead: its H2D overlaps this solve
+        const int ring = j % OR;
+        drain(ring);
+        if (j >= OR) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_out[ring], 0));  // device output slot is free
+        alg.solve(a % nslots, b % nslots, w, hh, h->d_flow[ring], (size_t)w * 2 * sizeof(float), h->s_compute);
+        if (bound > 0) {
+            launch_quantise(h->d_flow[ring], (size_t)w * 2 * sizeof(float), w, hh, bound, h->d_qx[ring], h->d_qy[ring], w,
+                            h->s_compute);
+            ++alg.launches;
+        }
+        DFB_CUDA(cudaEventRecord(h->ev_done[ring], h->s_compute));
+        DFB_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[ring], 0));
+        if (bound > 0) {
+            const bool direct = is_pinned_or_device(qx[j]) && is_pinned_or_device(qy[j]);
+            uint8_t *dx = direct ? qx[j] : h->h_q[ring], *dy = direct ? qy[j] : h->h_q[ring] + fbytes;
+            DFB_CUDA(cudaMemcpyAsync(dx, h->d_qx[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
+            DFB_CUDA(cudaMemcpyAsync(dy, h->d_qy[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
+            if (!direct) pending_copy[ring] = j;
+            h->counters.d2h_bytes += 2 * fbytes;
+        } else {
+            const bool direct = is_pinned_or_device(flows[j]);
+            DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : h->h_flow[ring], h->d_flow[ring], fbytes * 2 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, h->s_out));
+            if (!direct) pending_copy[ring] = j;
+            h->counters.d2h_bytes += fbytes * 2 * sizeof(float);
+        }
+        DFB_CUDA(cudaEventRecord(h->ev_out[ring], h->s_out));
+        ++h->counters.pairs;  // total_flows += 1 (:340)
+    }
+    DFB_CUDA(cudaStreamSynchronize(h->s_out));
+    for (int r = 0; r < OR; ++r) drain(r);
+    DFB_CUDA(cudaStreamSynchronize(h->s_compute));
+    return DFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dfb_version(void) {
+#ifdef DFB_STRICT_FP
+    return "denseflow_b200 0.1 (sm_100a, strict-fp)";
+#else
+    return "denseflow_b200 0.1 (sm_100a)";
+#endif
+}
+
+int dfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dfb_create(const char *algorithm, int device, int max_width, int max_height, dfb_handle **out) {
+    if (!out) return fail(nullptr, DFB_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (!algorithm) return fail(nullptr, DFB_ERR_INVALID_ARG, "algorithm is null");
+    const std::string alg(algorithm);
+    if (alg == "nv") return fail(nullptr, DFB_ERR_UNSUPPORTED, "NV hardware flow not enabled, pls recompile");
+    if (alg == "brox") return fail(nullptr, DFB_ERR_UNSUPPORTED, "brox is not supported in this build (tvl1 | farn)");
+    if (alg != "tvl1" && alg != "farn") return fail(nullptr, DFB_ERR_UNKNOWN_ALGORITHM, "unknown optical algorithm " + alg);
+    if (max_width <= 0 || max_height <= 0) return fail(nullptr, DFB_ERR_INVALID_ARG, "max_width/max_height must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, DFB_ERR_NO_DEVICE, "no CUDA device available (the engine has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, DFB_ERR_INVALID_ARG, "device index out of range");
+    dfb_handle *h = new dfb_handle();
+    h->device = device;
+    h->max_w = max_width;
+    h->max_h = max_height;
+    h->algorithm = alg;
+    const int rc = guarded(nullptr, [&]() {
+        DFB_CUDA(cudaSetDevice(device));
+        h->alg = alg == "tvl1" ? make_tvl1(device, max_width, max_height) : make_farneback(device, max_width, max_height);
+        return DFB_OK;
+    });
+    if (rc != DFB_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return DFB_OK;
+}
+
+void dfb_destroy(dfb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < dfb_handle::kFrameRing; ++i) {
+        if (h->d_frame[i]) cudaFree(h->d_frame[i]);
+        if (h->h_frame[i]) cudaFreeHost(h->h_frame[i]);
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_pyr[i]) cudaEventDestroy(h->ev_pyr[i]);
+    }
+    for (int i = 0; i < dfb_handle::kFlowRing; ++i) {
+        if (h->d_flow[i]) cudaFree(h->d_flow[i]);
+        if (h->d_qx[i]) cudaFree(h->d_qx[i]);
+        if (h->d_qy[i]) cudaFree(h->d_qy[i]);
+        if (h->h_flow[i]) cudaFreeHost(h->h_flow[i]);
+        if (h->h_q[i]) cudaFreeHost(h->h_q[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    h->alg.reset();
+    delete h;
+}
+
+const char *dfb_last_error(const dfb_handle *h) {
+    if (h) return h->last_error.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+int dfb_set_param(dfb_handle *h, const char *name, double value) {
+    if (!h || !name) return DFB_ERR_INVALID_ARG;
+    if (!h->alg->set_param(name, value)) return fail(h, DFB_ERR_INVALID_ARG, std::string("bad parameter ") + name);
+    return DFB_OK;
+}
+
+int dfb_get_param(const dfb_handle *h, const char *name, double *value) {
+    if (!h || !name || !value) return DFB_ERR_INVALID_ARG;
+    return h->alg->get_param(name, value) ? DFB_OK : DFB_ERR_INVALID_ARG;
+}
+
+int dfb_calc_device(dfb_handle *h, const uint8_t *a, size_t a_pitch, const uint8_t *b, size_t b_pitch, int width,
+                    int height, float *flow_xy, size_t flow_pitch, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!a || !b || !flow_xy) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (int rc = check_size(h, width, height)) return rc;
+    if (a_pitch < (size_t)width || b_pitch < (size_t)width || flow_pitch < (size_t)width * 8)
+        return fail(h, DFB_ERR_INVALID_ARG, "pitch smaller than a row");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        h->alg->prepare_frame(a, a_pitch, width, height, 0, s);
+        h->alg->prepare_frame(b, b_pitch, width, height, 1, s);
+        h->alg->solve(0, 1, width, height, flow_xy, flow_pitch, s);
+        ++h->counters.pairs;
+        return DFB_OK;
+    });
+}
+
+int dfb_calc_host(dfb_handle *h, const uint8_t *a, const uint8_t *b, int width, int height, float *flow_xy) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!a || !b || !flow_xy) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    const uint8_t *frames[2] = {a, b};
+    float *flows[1] = {flow_xy};
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        return batch_host(h, frames, 2, 1, width, height, flows, 0, nullptr, nullptr);
+    });
+}
+
+int dfb_calc_batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int step, int width, int height,
+                        float *const *flows) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (n_frames > std::abs(step) && !flows) return fail(h, DFB_ERR_INVALID_ARG, "flows is null");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        return batch_host(h, frames, n_frames, step, width, height, flows, 0, nullptr, nullptr);
+    });
+}
+
+int dfb_calc_batch_host_u8(dfb_handle *h, const uint8_t *const *frames, int n_frames, int step, int width, int height,
+                           int bound, uint8_t *const *qx, uint8_t *const *qy) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (bound <= 0) return fail(h, DFB_ERR_INVALID_ARG, "bound should > 0!");  // check_param, src/denseflow_gpu.cpp:15-18
+    if (n_frames > std::abs(step) && (!qx || !qy)) return fail(h, DFB_ERR_INVALID_ARG, "qx/qy is null");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        return batch_host(h, frames, n_frames, step, width, height, nullptr, bound, qx, qy);
+    });
+}
+
+int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, int step, int width, int height,
+                          float *flows, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (int rc = check_size(h, width, height)) return rc;
+    if (step == 0) return fail(h, DFB_ERR_INVALID_ARG, "step must be non-zero for flow extraction");
+    const int astep = std::abs(step);
+    const int M = std::max(n_frames - astep, 0);
+    if (M == 0) return DFB_OK;
+    if (!frames || !flows) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        FlowAlgorithm &alg = *h->alg;
+        alg.ensure_slots(astep + 2);
+        const int nslots = alg.num_slots();
+        const size_t fbytes = (size_t)width * height;
+        int prepared = 0;
+        for (int j = 0; j < M; ++j) {
+            const int a = step > 0 ? j : j + astep;
+            const int b = step > 0 ? j + astep : j;
+            for (; prepared <= std::max(a, b); ++prepared)
+                alg.prepare_frame(frames + (size_t)prepared * fbytes, width, width, height, prepared % nslots, s);
+            alg.solve(a % nslots, b % nslots, width, height, flows + (size_t)j * fbytes * 2, (size_t)width * 8, s);
+            ++h->counters.pairs;
+        }
+        return DFB_OK;
+    });
+}
+
+int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, int width, int height, int bound,
+                        uint8_t *qx, uint8_t *qy, size_t q_pitch, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!flow_xy || !qx || !qy) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (bound <= 0) return fail(h, DFB_ERR_INVALID_ARG, "bound should > 0!");
+    if (width <= 0 || height <= 0) return fail(h, DFB_ERR_INVALID_ARG, "width/height must be positive");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        launch_quantise(flow_xy, flow_pitch, width, height, bound, qx, qy, q_pitch, static_cast<cudaStream_t>(stream));
+        ++h->alg->launches;
+        return DFB_OK;
+    });
+}
+
+int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out) {
+    if (!h || !out) return DFB_ERR_INVALID_ARG;
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        h->alg->tvl1_stats(out);
+        return DFB_OK;
+    });
+}
+
+int dfb_get_counters(dfb_handle *h, dfb_counters *out) {
+    if (!h || !out) return DFB_ERR_INVALID_ARG;
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        dfb_tvl1_stats st;
+        h->alg->tvl1_stats(&st);  // folds a pending fused-kernel log into pixel_iters
+        *out = h->counters;
+        out->kernel_launches = h->alg->launches;
+        out->pixel_iters = h->alg->pixel_iters;
+        return DFB_OK;
+    });
+}
+
+int dfb_reset_counters(dfb_handle *h) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    h->counters = dfb_counters{};
+    h->alg->launches = 0;
+    h->alg->pixel_iters = 0;
+    return DFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// engine.h — host-side engine objects behind the C ABI (include/denseflow_b200.h).
+// FlowEngine is the replacement for the cv::cuda::DenseOpticalFlow object the reference creates at
+// /root/reference/src/denseflow_gpu.cpp:299-301 and calls at :327/:329.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/denseflow_b200.h"
+#include "common.cuh"
+
+namespace dfb {
+
+struct LevelGeom {
+    int w, h, pitch;
+};
+
+// Algorithm back-end working on device buffers. One frame "slot" holds everything that depends on
+// a single frame (its fp32 pyramid), so a frame shared by two consecutive pairs is prepared once.
+class FlowAlgorithm {
+  public:
+    virtual ~FlowAlgorithm() = default;
+    virtual const char *name() const = 0;
+    virtual int num_slots() const = 0;
+    virtual void ensure_slots(int n) = 0;
+    // per-frame work: u8 -> fp32 (+ pyramid)
+    virtual void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) = 0;
+    // per-pair work: flow(slot_a -> slot_b) into interleaved float2 rows
+    virtual void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes,
+                       cudaStream_t s) = 0;
+    virtual bool set_param(const std::string &name, double v) = 0;
+    virtual bool get_param(const std::string &name, double *v) const = 0;
+    virtual void tvl1_stats(dfb_tvl1_stats *out) { *out = dfb_tvl1_stats{}; }
+    uint64_t launches = 0;     // kernels launched
+    uint64_t pixel_iters = 0;  // tvl1: sum of level pixels over executed inner iterations
+};
+
+std::unique_ptr<FlowAlgorithm> make_tvl1(int device, int max_w, int max_h);
+std::unique_ptr<FlowAlgorithm> make_farneback(int device, int max_w, int max_h);
+
+}  // namespace dfb

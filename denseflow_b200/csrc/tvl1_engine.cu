@@ -1,0 +1,346 @@
+// tvl1_engine.cu — host orchestration of the TV-L1 path: the replacement for
+// cv::cuda::OpticalFlowDual_TVL1 as created/called at /root/reference/src/denseflow_gpu.cpp:299,327
+// (control flow per SURVEY.md Appendix A.1, A.2, A.4, A.5).
+//
+// Two schedules over the same arithmetic:
+//   fused = 1 (default)  one persistent cooperative kernel per pair (tvl1_fused.cu): gradients,
+//                        warps, the primal/dual iterations with k steps kept on chip per tile, the
+//                        A.4 convergence state machine and the flow upsampling all run on-device
+//                        with no host round trip.
+//   fused = 0            one kernel per half-step, the reference's launch structure, with the A.4
+//                        state machine on the host (one stream sync per convergence check).
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+#include "tvl1.cuh"
+#include "tvl1_fused.cuh"
+
+namespace dfb {
+
+namespace {
+
+constexpr int kMaxScales = 16;
+
+struct Tvl1Params {
+    double tau = 0.25, lambda = 0.15, theta = 0.3;
+    int nscales = 5, warps = 5;
+    double epsilon = 0.01;
+    int iterations = 300;
+    double scale_step = 0.8;
+    int fused = 0;
+    int fused_k = 8;
+};
+
+class Tvl1 final : public FlowAlgorithm {
+  public:
+    Tvl1(int device, int max_w, int max_h) : device_(device), max_w_(max_w), max_h_(max_h) {
+        DFB_CUDA(cudaSetDevice(device_));
+        allocate();
+    }
+    ~Tvl1() override {
+        cudaSetDevice(device_);
+        for (auto p : extra_slots_) cudaFree(p);
+        if (host_ctl_) cudaFreeHost(host_ctl_);
+    }
+    const char *name() const override { return "tvl1"; }
+    int num_slots() const override { return (int)slots_.size(); }
+
+    void ensure_slots(int n) override {
+        while ((int)slots_.size() < n) {
+            float *p = nullptr;
+            DFB_CUDA(cudaMalloc(&p, pyr_elems_ * sizeof(float)));
+            extra_slots_.push_back(p);
+            slots_.push_back(p);
+        }
+    }
+
+    bool set_param(const std::string &k, double v) override {
+        if (k == "tau") prm_.tau = v;
+        else if (k == "lambda") prm_.lambda = v;
+        else if (k == "theta") prm_.theta = v;
+        else if (k == "nscales") { if (v < 1 || v > kMaxScales) return false; prm_.nscales = (int)v; }
+        else if (k == "warps") { if (v < 1 || v > 16) return false; prm_.warps = (int)v; }
+        else if (k == "epsilon") prm_.epsilon = v;
+        else if (k == "iterations") { if (v < 1) return false; prm_.iterations = (int)v; }
+        else if (k == "scale_step") { if (!(v > 0 && v < 1)) return false; prm_.scale_step = v; }
+        else if (k == "fused") prm_.fused = v != 0;
+        else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
+        else return false;
+        return true;
+    }
+    bool get_param(const std::string &k, double *v) const override {
+        if (k == "tau") *v = prm_.tau;
+        else if (k == "lambda") *v = prm_.lambda;
+        else if (k == "theta") *v = prm_.theta;
+        else if (k == "nscales") *v = prm_.nscales;
+        else if (k == "warps") *v = prm_.warps;
+        else if (k == "epsilon") *v = prm_.epsilon;
+        else if (k == "iterations") *v = prm_.iterations;
+        else if (k == "scale_step") *v = prm_.scale_step;
+        else if (k == "fused") *v = prm_.fused;
+        else if (k == "fused_k") *v = prm_.fused_k;
+        else return false;
+        return true;
+    }
+
+    // A.1: level sizes = round-half-even(dim * scaleStep); a level with cols<16 || rows<16 is dropped.
+    int level_geometry(int w, int h, LevelGeom *lv) const {
+        int n = 1;
+        lv[0] = {w, h, round_up(w, 32)};
+        for (int s = 1; s < prm_.nscales; ++s) {
+            const int nw = (int)std::nearbyint((double)lv[s - 1].w * prm_.scale_step);
+            const int nh = (int)std::nearbyint((double)lv[s - 1].h * prm_.scale_step);
+            if (nw < 16 || nh < 16) break;
+            lv[s] = {nw, nh, round_up(nw, 32)};
+            n = s + 1;
+        }
+        return n;
+    }
+
+    void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) override {
+        LevelGeom lv[kMaxScales];
+        const int n = level_geometry(w, h, lv);
+        float *base = slots_.at(slot);
+        launch_u8_to_f32(src, pitch_bytes, level_plane(base, lv, 0), s);
+        ++launches;
+        const float finv = (float)(1.0 / prm_.scale_step);  // dsize empty => fx = float(1/scaleStep)
+        for (int l = 1; l < n; ++l) {
+            launch_resize_linear(level_plane(base, lv, l - 1), level_plane(base, lv, l), finv, finv, 1.0f, s);
+            ++launches;
+        }
+    }
+
+    void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes,
+               cudaStream_t s) override {
+        LevelGeom lv[kMaxScales];
+        const int n = level_geometry(w, h, lv);
+        last_nscales_ = n;
+        std::memcpy(last_lv_, lv, sizeof(lv));
+        if (prm_.fused)
+            solve_fused(slot_a, slot_b, lv, n, flow_xy, flow_pitch_bytes, s);
+        else
+            solve_unfused(slot_a, slot_b, lv, n, flow_xy, flow_pitch_bytes, s);
+    }
+
+    void tvl1_stats(dfb_tvl1_stats *out) override {
+        *out = dfb_tvl1_stats{};
+        if (stats_pending_) {  // fused engine: the log was written by the kernel into mapped host memory
+            DFB_CUDA(cudaEventSynchronize(stats_event_));
+            for (int i = 0; i < 16 * 16; ++i) last_iters_[i] = host_ctl_->iters[i];
+            stats_pending_ = false;
+            accumulate_pixel_iters();
+        }
+        out->nscales = last_nscales_;
+        out->warps = prm_.warps;
+        for (int s = 0; s < last_nscales_; ++s) {
+            out->level_w[s] = last_lv_[s].w;
+            out->level_h[s] = last_lv_[s].h;
+        }
+        std::memcpy(out->iters, last_iters_, sizeof(last_iters_));
+    }
+
+  private:
+    Plane level_plane(float *base, const LevelGeom *lv, int l) const {
+        size_t off = 0;
+        for (int i = 0; i < l; ++i) off += level_stride(i);
+        return Plane{base + off, lv[l].w, lv[l].h, lv[l].pitch};
+    }
+    // slot layout is fixed by the MAX geometry so any smaller frame fits
+    size_t level_stride(int l) const { return max_lv_elems_[l]; }
+
+    void allocate() {
+        // geometry of the largest frame, with the full default pyramid depth available
+        Tvl1Params keep = prm_;
+        prm_.nscales = kMaxScales;
+        LevelGeom lv[kMaxScales];
+        const int n = level_geometry(max_w_, max_h_, lv);
+        prm_ = keep;
+        pyr_elems_ = 0;
+        for (int l = 0; l < kMaxScales; ++l) {
+            // +pitch: one spare row so float4 tile reads one row past the image stay inside the slab
+            max_lv_elems_[l] = l < n ? (size_t)lv[l].pitch * (lv[l].h + 1) : 0;
+            max_lv_elems_[l] = (max_lv_elems_[l] + 63) & ~size_t(63);
+            pyr_elems_ += max_lv_elems_[l];
+        }
+        plane_elems_ = (size_t)lv[0].pitch * (lv[0].h + 1);
+        constexpr int kInitialSlots = 4;
+        const int n_work = 2 /*I1x,I1y*/ + 4 /*consts*/ + 12 /*u,p ping-pong*/;
+        size_t bytes = 0;
+        bytes += kInitialSlots * Slab::padded(pyr_elems_, 4);
+        bytes += 2 * 2 * Slab::padded(pyr_elems_, 4);  // u1s,u2s pyramids, two buffers each
+        bytes += n_work * Slab::padded(plane_elems_, 4);
+        bytes += Slab::padded(kMaxPartials, 8) + Slab::padded(64, 8) + (1 << 16);
+        slab_.reserve(bytes);
+        for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(pyr_elems_));
+        for (int b = 0; b < 2; ++b) {
+            u1pyr_[b] = slab_.take<float>(pyr_elems_);
+            u2pyr_[b] = slab_.take<float>(pyr_elems_);
+        }
+        I1x_ = slab_.take<float>(plane_elems_);
+        I1y_ = slab_.take<float>(plane_elems_);
+        I1wx_ = slab_.take<float>(plane_elems_);
+        I1wy_ = slab_.take<float>(plane_elems_);
+        grad_ = slab_.take<float>(plane_elems_);
+        rho_c_ = slab_.take<float>(plane_elems_);
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < 4; ++k) p_[b][k] = slab_.take<float>(plane_elems_);
+        partials_ = slab_.take<double>(kMaxPartials);
+        sync_words_ = slab_.take<unsigned>(64);
+        DFB_CUDA(cudaHostAlloc(&host_ctl_, sizeof(FusedHostCtl), cudaHostAllocMapped));
+        std::memset(host_ctl_, 0, sizeof(FusedHostCtl));
+        DFB_CUDA(cudaHostGetDevicePointer(&dev_ctl_, host_ctl_, 0));
+        DFB_CUDA(cudaEventCreateWithFlags(&stats_event_, cudaEventDisableTiming));
+        // every plane starts finite: padding columns are read (never used) by vectorised kernels
+        slab_.zero();
+    }
+
+    Plane work(float *p, const LevelGeom &g) const { return Plane{p, g.w, g.h, g.pitch}; }
+
+    // ---- fused = 0: reference launch structure, A.4 state machine on the host ------------------
+    void solve_unfused(int slot_a, int slot_b, const LevelGeom *lv, int n, float *flow_xy, size_t flow_pitch_bytes,
+                       cudaStream_t s) {
+        const Tvl1Consts c{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
+        std::memset(last_iters_, 0, sizeof(last_iters_));
+        float *I0b = slots_.at(slot_a), *I1b = slots_.at(slot_b);
+        for (int l = n - 1; l >= 0; --l) {
+            const LevelGeom &g = lv[l];
+            const Plane I0 = level_plane(I0b, lv, l), I1 = level_plane(I1b, lv, l);
+            const Plane u1 = level_plane(u1pyr_[0], lv, l), u2 = level_plane(u2pyr_[0], lv, l);
+            const Plane I1x = work(I1x_, g), I1y = work(I1y_, g), I1wx = work(I1wx_, g), I1wy = work(I1wy_, g);
+            const Plane grad = work(grad_, g), rho_c = work(rho_c_, g);
+            const Plane p11 = work(p_[0][0], g), p12 = work(p_[0][1], g), p21 = work(p_[0][2], g), p22 = work(p_[0][3], g);
+            if (l == n - 1) {  // useInitialFlow = false
+                launch_fill(u1, 0.f, s);
+                launch_fill(u2, 0.f, s);
+                launches += 2;
+            }
+            launch_centered_gradient(I1, I1x, I1y, s);
+            launch_fill(p11, 0.f, s);  // once per scale, not per warp (A.2 step 2)
+            launch_fill(p12, 0.f, s);
+            launch_fill(p21, 0.f, s);
+            launch_fill(p22, 0.f, s);
+            launches += 5;
+            const double scaled_eps = prm_.epsilon * prm_.epsilon * (double)((long)g.w * g.h);
+            const int nblk = estimate_u_blocks(g.w, g.h);
+            for (int wi = 0; wi < prm_.warps; ++wi) {
+                launch_warp_backward(I0, I1, I1x, I1y, u1, u2, I1wx, I1wy, grad, rho_c, s);
+                ++launches;
+                double error = DBL_MAX, prev_error = 0.0;
+                int it = 0;
+                for (; error > scaled_eps && it < prm_.iterations; ++it) {
+                    const bool calc_error = prm_.epsilon > 0 && (it & 1) && prev_error < scaled_eps;
+                    launch_estimate_u(I1wx, I1wy, grad, rho_c, p11, p12, p21, p22, u1, u2, c,
+                                      calc_error ? partials_ : nullptr, s);
+                    ++launches;
+                    if (calc_error) {
+                        launch_sum_partials(partials_, nblk, &dev_ctl_->error, s);
+                        ++launches;
+                        DFB_CUDA(cudaStreamSynchronize(s));  // the reference syncs here too (stream.waitForCompletion)
+                        error = host_ctl_->error;
+                        prev_error = error;
+                    } else {
+                        error = DBL_MAX;
+                        prev_error -= scaled_eps;
+                    }
+                    launch_estimate_dual(u1, u2, p11, p12, p21, p22, c, s);
+                    ++launches;
+                }
+                last_iters_[l * prm_.warps + wi] = it;
+            }
+            if (l > 0) {  // A.2 step 4: explicit dsize => f = float(1 / (dst/src)); then * float(1/scaleStep)
+                const float ufx = (float)(1.0 / ((double)lv[l - 1].w / (double)g.w));
+                const float ufy = (float)(1.0 / ((double)lv[l - 1].h / (double)g.h));
+                const float mul = (float)(1.0 / prm_.scale_step);
+                launch_resize_linear(u1, level_plane(u1pyr_[0], lv, l - 1), ufx, ufy, mul, s);
+                launch_resize_linear(u2, level_plane(u2pyr_[0], lv, l - 1), ufx, ufy, mul, s);
+                launches += 2;
+            }
+        }
+        launch_merge_flow(level_plane(u1pyr_[0], lv, 0), level_plane(u2pyr_[0], lv, 0), flow_xy, flow_pitch_bytes, s);
+        ++launches;
+        stats_pending_ = false;
+        accumulate_pixel_iters();
+    }
+
+    // ---- fused = 1 -------------------------------------------------------------------------------
+    void solve_fused(int slot_a, int slot_b, const LevelGeom *lv, int n, float *flow_xy, size_t flow_pitch_bytes,
+                     cudaStream_t s) {
+        FusedJob job{};
+        job.nscales = n;
+        job.warps = prm_.warps;
+        job.iterations = prm_.iterations;
+        job.epsilon = prm_.epsilon;
+        job.k = prm_.fused_k;
+        job.c = Tvl1Consts{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
+        job.up_mul = (float)(1.0 / prm_.scale_step);
+        for (int l = 0; l < n; ++l) {
+            FusedLevel &L = job.lv[l];
+            L.w = lv[l].w;
+            L.h = lv[l].h;
+            L.pitch = lv[l].pitch;
+            L.I0 = level_plane(slots_.at(slot_a), lv, l).p;
+            L.I1 = level_plane(slots_.at(slot_b), lv, l).p;
+            for (int b = 0; b < 2; ++b) {
+                L.u1[b] = level_plane(u1pyr_[b], lv, l).p;
+                L.u2[b] = level_plane(u2pyr_[b], lv, l).p;
+            }
+            if (l > 0) {
+                L.up_fx = (float)(1.0 / ((double)lv[l - 1].w / (double)lv[l].w));
+                L.up_fy = (float)(1.0 / ((double)lv[l - 1].h / (double)lv[l].h));
+            }
+        }
+        job.I1x = I1x_;
+        job.I1y = I1y_;
+        job.I1wx = I1wx_;
+        job.I1wy = I1wy_;
+        job.grad = grad_;
+        job.rho_c = rho_c_;
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < 4; ++k) job.p[b][k] = p_[b][k];
+        job.partials = partials_;
+        job.sync = sync_words_;
+        job.ctl = dev_ctl_;
+        job.flow_xy = flow_xy;
+        job.flow_pitch_bytes = flow_pitch_bytes;
+        launches += launch_tvl1_fused(job, device_, s);
+        DFB_CUDA(cudaEventRecord(stats_event_, s));
+        stats_pending_ = true;
+    }
+
+    void accumulate_pixel_iters() {
+        for (int l = 0; l < last_nscales_; ++l)
+            for (int wi = 0; wi < prm_.warps; ++wi)
+                pixel_iters += (uint64_t)last_iters_[l * prm_.warps + wi] * (uint64_t)last_lv_[l].w * last_lv_[l].h;
+    }
+
+    static constexpr size_t kMaxPartials = 1 << 16;
+
+    int device_, max_w_, max_h_;
+    Tvl1Params prm_;
+    Slab slab_;
+    std::vector<float *> slots_;
+    std::vector<float *> extra_slots_;
+    size_t max_lv_elems_[kMaxScales] = {};
+    size_t pyr_elems_ = 0, plane_elems_ = 0;
+    float *u1pyr_[2] = {}, *u2pyr_[2] = {};
+    float *I1x_ = nullptr, *I1y_ = nullptr, *I1wx_ = nullptr, *I1wy_ = nullptr, *grad_ = nullptr, *rho_c_ = nullptr;
+    float *p_[2][4] = {};
+    double *partials_ = nullptr;
+    unsigned *sync_words_ = nullptr;
+    FusedHostCtl *host_ctl_ = nullptr, *dev_ctl_ = nullptr;
+    cudaEvent_t stats_event_ = nullptr;
+    bool stats_pending_ = false;
+    int last_nscales_ = 0;
+    LevelGeom last_lv_[kMaxScales] = {};
+    int last_iters_[16 * 16] = {};
+};
+
+}  // namespace
+
+std::unique_ptr<FlowAlgorithm> make_tvl1(int device, int max_w, int max_h) {
+    return std::unique_ptr<FlowAlgorithm>(new Tvl1(device, max_w, max_h));
+}
+
+}  // namespace dfb

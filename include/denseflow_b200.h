@@ -1,0 +1,137 @@
+/*
+ * denseflow_b200.h — C ABI of the B200-native dense optical-flow engine.
+ *
+ * This is the drop-in boundary for the one hot path of open-mmlab/denseflow: the body of the
+ * per-pair loop in DenseFlow::calc_optflows_imp (/root/reference/src/denseflow_gpu.cpp:313-342).
+ * The reference has no FFI layer; what it binds there is the OpenCV algorithm-object interface.
+ * Each entry point below names the reference call it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns an int status
+ * (0 = DFB_OK, negative = error) and never throws; dfb_last_error() gives the message the C++ host
+ * rethrows as std::runtime_error (reference behaviour: message + exit 1, tools/denseflow.cpp:93-96).
+ * A handle is single-threaded (reference: one thread calls create/calc/release,
+ * include/dense_flow.h:78); handles on different threads/devices are independent.  Every call
+ * selects the handle's device itself.
+ */
+#ifndef DENSEFLOW_B200_H
+#define DENSEFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dfb_handle dfb_handle;
+
+enum {
+    DFB_OK = 0,
+    DFB_ERR_INVALID_ARG = -1,
+    DFB_ERR_UNKNOWN_ALGORITHM = -2, /* reference: std::runtime_error("unknown optical algorithm ...") src/denseflow_gpu.cpp:336 */
+    DFB_ERR_CUDA = -3,
+    DFB_ERR_SIZE = -4,              /* frame larger than max_width x max_height given at create, or a/b mismatch */
+    DFB_ERR_UNSUPPORTED = -5,       /* "nv" / "brox": outside this build (reference: "not enabled, pls recompile" :296) */
+    DFB_ERR_NO_DEVICE = -6
+};
+
+/* Library / device probes (no reference equivalent; setDevice(0) is hard-wired at src/denseflow_gpu.cpp:482). */
+const char *dfb_version(void);
+int dfb_device_count(void);
+
+/*
+ * Factory.  Replaces  cuda::OpticalFlowDual_TVL1::create()   src/denseflow_gpu.cpp:299   (algorithm = "tvl1")
+ *           and       cuda::FarnebackOpticalFlow::create()    src/denseflow_gpu.cpp:301   (algorithm = "farn")
+ * with the argument-less upstream defaults (tvl1: tau .25, lambda .15, theta .3, nscales 5, warps 5,
+ * epsilon .01, iterations 300, scaleStep .8; farn: numLevels 5, pyrScale .5, winSize 13, numIters 10,
+ * polyN 5, polySigma 1.1, flags 0).  All device workspace for frames up to max_width x max_height is
+ * allocated here, once (the reference re-creates the algorithm object per <=512-frame batch, :299-301,:349-352).
+ */
+int dfb_create(const char *algorithm, int device, int max_width, int max_height, dfb_handle **out);
+
+/* Replaces alg.release()  src/denseflow_gpu.cpp:345-355. */
+void dfb_destroy(dfb_handle *h);
+
+/* Message of the last failing call on this handle (or of the last failing dfb_create when h == NULL). */
+const char *dfb_last_error(const dfb_handle *h);
+
+/*
+ * Algorithm hyper-parameters.  The reference never sets any (always create() defaults); these exist
+ * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations"
+ * "scale_step"; engine knobs: "fused" (1 = persistent fused primal+dual kernel [default], 0 = one
+ * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile).
+ */
+int dfb_set_param(dfb_handle *h, const char *name, double value);
+int dfb_get_param(const dfb_handle *h, const char *name, double *value);
+
+/*
+ * Compute, device buffers.  Replaces  alg->calc(gray_a, gray_b, flow_gpu, stream)  src/denseflow_gpu.cpp:327 / :329.
+ *   a, b      : CV_8UC1 frames in device memory, row pitch in bytes (GpuMat pitch)
+ *   flow_xy   : CV_32FC2 (u, v interleaved) in device memory, row pitch in bytes; u = x displacement
+ *   stream    : cudaStream_t the work is enqueued on (the reference's DenseFlow::stream, include/dense_flow.h:33)
+ * Asynchronous w.r.t. the host apart from the convergence read-back of the non-fused engine.
+ */
+int dfb_calc_device(dfb_handle *h, const uint8_t *a, size_t a_pitch, const uint8_t *b, size_t b_pitch, int width,
+                    int height, float *flow_xy, size_t flow_pitch, void *stream);
+
+/*
+ * Compute, host buffers: upload a and b, calc, download the flow — the three statements
+ * src/denseflow_gpu.cpp:317-318, :327/:329, :339 as one call.  Buffers are dense (pitch = width) and may be
+ * pageable; the engine stages through its own pinned ring.  Blocks until flow_xy is complete.
+ */
+int dfb_calc_host(dfb_handle *h, const uint8_t *a, const uint8_t *b, int width, int height, float *flow_xy);
+
+/*
+ * The shape calc_optflows_imp really has (src/denseflow_gpu.cpp:307-342): N gray frames, step s,
+ * M = max(N - |s|, 0) flows with pair (a, b) = (i, i+s) for s > 0 and (i-s, i) for s < 0 (:315-316).
+ * Each frame is uploaded and pyramided once (the reference does both twice), and copies overlap compute.
+ *   frames[n_frames] : host pointers, dense width*height uint8
+ *   flows[M]         : host pointers, dense width*height*2 float (CV_32FC2)
+ */
+int dfb_calc_batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int step, int width, int height,
+                        float *const *flows);
+
+/*
+ * Same batch, but the flow is bounded + quantised on the device and only the two uint8 planes come
+ * back: fuses convertFlowToImage (src/common.cpp:4-16, via encodeFlowMap :48-64 with
+ * lowerBound = -bound, higherBound = +bound) into the epilogue.  Bit-exact to the CAST macro.
+ *   qx[M], qy[M] : host pointers, dense width*height uint8
+ */
+int dfb_calc_batch_host_u8(dfb_handle *h, const uint8_t *const *frames, int n_frames, int step, int width, int height,
+                           int bound, uint8_t *const *qx, uint8_t *const *qy);
+
+/* Device-resident batch: frames is one device allocation [n_frames][height][width] uint8 (dense),
+ * flows one device allocation [M][height][width][2] float.  Enqueued on `stream`. */
+int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, int step, int width, int height,
+                          float *flows, void *stream);
+
+/* Stand-alone quantiser on device buffers (src/common.cpp:4-16).  flow_xy pitch in bytes. */
+int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, int width, int height, int bound,
+                        uint8_t *qx, uint8_t *qy, size_t q_pitch, void *stream);
+
+/*
+ * Work counters of the most recent calc on this handle (for the roofline arithmetic):
+ *   iters[nscales*warps] executed inner iterations per (scale, warp), index s*warps + w, s = 0 finest
+ *   level_w/level_h[nscales] pyramid sizes
+ * dfb_get_counters: cumulative since create / last reset.
+ */
+typedef struct {
+    int nscales, warps;
+    int level_w[16], level_h[16];
+    int iters[16 * 16];
+} dfb_tvl1_stats;
+int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out);
+
+typedef struct {
+    uint64_t pairs;          /* flow fields computed */
+    uint64_t kernel_launches; /* CUDA kernels launched by this handle */
+    uint64_t pixel_iters;    /* sum over executed inner iterations of level pixels (tvl1) */
+    uint64_t h2d_bytes, d2h_bytes;
+} dfb_counters;
+int dfb_get_counters(dfb_handle *h, dfb_counters *out);
+int dfb_reset_counters(dfb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSEFLOW_B200_H */
