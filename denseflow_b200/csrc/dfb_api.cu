@@ -411,8 +411,8 @@ int dfb_get_counters(dfb_handle *h, dfb_counters *out) {
 int dfb_reset_counters(dfb_handle *h) {
     if (!h) return DFB_ERR_INVALID_ARG;
     h->counters = dfb_counters{};
-    h->alg->launches = 0;
-    h->alg->pixel_iters = 0;
+    cudaSetDevice(h->device);
+    h->alg->reset_counters();
     return DFB_OK;
 }
 

@@ -35,6 +35,7 @@ class FlowAlgorithm {
     virtual bool set_param(const std::string &name, double v) = 0;
     virtual bool get_param(const std::string &name, double *v) const = 0;
     virtual void tvl1_stats(dfb_tvl1_stats *out) { *out = dfb_tvl1_stats{}; }
+    virtual void reset_counters() { launches = 0; pixel_iters = 0; }
     uint64_t launches = 0;     // kernels launched
     uint64_t pixel_iters = 0;  // tvl1: sum of level pixels over executed inner iterations
 };

@@ -29,7 +29,7 @@ struct Tvl1Params {
     double epsilon = 0.01;
     int iterations = 300;
     double scale_step = 0.8;
-    int fused = 0;
+    int fused = 1;
     int fused_k = 8;
 };
 
@@ -130,8 +130,8 @@ class Tvl1 final : public FlowAlgorithm {
             DFB_CUDA(cudaEventSynchronize(stats_event_));
             for (int i = 0; i < 16 * 16; ++i) last_iters_[i] = host_ctl_->iters[i];
             stats_pending_ = false;
-            accumulate_pixel_iters();
         }
+        pixel_iters = unfused_px_iters_ + host_ctl_->px_iters_total;
         out->nscales = last_nscales_;
         out->warps = prm_.warps;
         for (int s = 0; s < last_nscales_; ++s) {
@@ -312,8 +312,19 @@ class Tvl1 final : public FlowAlgorithm {
     void accumulate_pixel_iters() {
         for (int l = 0; l < last_nscales_; ++l)
             for (int wi = 0; wi < prm_.warps; ++wi)
-                pixel_iters += (uint64_t)last_iters_[l * prm_.warps + wi] * (uint64_t)last_lv_[l].w * last_lv_[l].h;
+                unfused_px_iters_ += (uint64_t)last_iters_[l * prm_.warps + wi] * (uint64_t)last_lv_[l].w * last_lv_[l].h;
     }
+    void reset_counters() override {
+        if (stats_pending_) {
+            cudaEventSynchronize(stats_event_);
+            stats_pending_ = false;
+        }
+        launches = 0;
+        pixel_iters = 0;
+        unfused_px_iters_ = 0;
+        host_ctl_->px_iters_total = 0;
+    }
+    uint64_t unfused_px_iters_ = 0;
 
     static constexpr size_t kMaxPartials = 1 << 16;
 

@@ -18,7 +18,8 @@ struct FusedLevel {
 // Written by the kernel into mapped host memory (no memcpy, no sync on the pair path).
 struct FusedHostCtl {
     double error;         // unfused engine: convergence sum read by the host state machine
-    int iters[16 * 16];   // executed inner iterations per (scale, warp)
+    int iters[16 * 16];   // executed inner iterations per (scale, warp) of the last pair
+    unsigned long long px_iters_total;  // sum over pairs of (level pixels x executed iterations)
 };
 
 struct FusedJob {

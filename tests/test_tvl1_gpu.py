@@ -45,18 +45,23 @@ def test_pair256_matches_oracle(oracle, pair256, variant, fused):
 
 @pytest.mark.parametrize("fused", FUSED)
 def test_iteration_cap_pair(oracle, fused):
-    """Independent textures: never converges, every warp hits the 300-iteration cap at coarse scales."""
+    """Independent textures never converge: every (scale, warp) runs into the iteration cap.  The cap is
+    lowered to 40 (2 scales x 2 warps) so fp32 chaos cannot build up and the comparison stays tight."""
     a, b = synth.noise_pair(128, 160, 7)
-    ref, ref_log = oracle.tvl1_calc(a, b, return_iters=True)
-    e = _engine("strict", 160, 128, fused=fused)
+    prm = oracle.tvl1_params(iterations=40, nscales=2, warps=2)
+    ref, ref_log = oracle.tvl1_calc(a, b, prm, return_iters=True)
+    e = _engine("strict", 160, 128, fused=fused, iterations=40, nscales=2, warps=2)
     flow = e.calc(a, b)
     iters, _ = e.tvl1_stats()
     print("cap pair iters", iters.tolist(), ref_log.tolist())
-    assert iters.max() == 300
+    assert (iters == 40).all() and (ref_log == 40).all()
     assert np.isfinite(flow).all()
-    # a non-converging problem is chaotic in fp32: compare loosely, on the median end-point error
-    d = np.hypot(*(np.moveaxis(flow - ref, -1, 0)))
-    assert np.median(d) < 0.05
+    assert synth.aee(flow, ref) < 1e-3
+    # full default run: the 300 cap is reached and the result stays finite
+    e2 = _engine("default", 160, 128, fused=fused)
+    f2 = e2.calc(a, b)
+    it2, _ = e2.tvl1_stats()
+    assert it2.max() == 300 and np.isfinite(f2).all()
 
 
 @pytest.mark.parametrize("fused", FUSED)
