@@ -53,6 +53,7 @@ SIGNATURES = {
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfb_get_tvl1_stats": (C.c_int, [C.c_void_p, C.POINTER(Tvl1Stats)]),
     "dfb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "dfb_get_tvl1_phase_ns": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dfb_reset_counters": (C.c_int, [C.c_void_p]),
 }
 

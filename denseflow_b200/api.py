@@ -130,7 +130,6 @@ class DenseOpticalFlow:
     def tvl1_stats(self):
         st = _lib.Tvl1Stats()
         self._check(self._L.dfb_get_tvl1_stats(self._h, C.byref(st)))
-        iters = np.array(st.iters[:], np.int64).reshape(16, 16)[:st.nscales, :st.warps] if st.warps else None
         # rows of the C array are indexed s*warps + w
         flat = np.array(st.iters[:], np.int64)
         iters = flat[:st.nscales * st.warps].reshape(st.nscales, st.warps)
@@ -141,6 +140,14 @@ class DenseOpticalFlow:
         c = _lib.Counters()
         self._check(self._L.dfb_get_counters(self._h, C.byref(c)))
         return {k: getattr(c, k) for k, _ in c._fields_}
+
+    def phase_ns(self):
+        buf = (C.c_uint64 * 32)()
+        self._check(self._L.dfb_get_tvl1_phase_ns(self._h, buf))
+        v = list(buf)
+        return {"level_start": v[0], "warp": v[1], "tiles": v[2], "barrier": v[3], "upsample_merge": v[4],
+                "tile_load": v[5], "tile_iter": v[6], "tile_store": v[7],
+                "tiles_per_scale": v[8:16], "chunks_per_scale": v[16:24]}
 
     def reset_counters(self):
         self._check(self._L.dfb_reset_counters(self._h))
@@ -167,8 +174,3 @@ def create(algorithm, device=0, max_width=1920, max_height=1080, variant="defaul
     if algorithm == "farn":
         return FarnebackOpticalFlow.create(device, max_width, max_height, variant)
     return DenseOpticalFlow(algorithm, device, max_width, max_height, variant)  # raises with the reference's message
-
-
-def convert_flow_to_image(flow, bound):
-    """Not provided on the host: the quantiser runs on the GPU (calc_batch(bound=...) / quantise_device)."""
-    raise NotImplementedError("use calc_batch(..., bound=B) or DenseOpticalFlow.quantise_device")

@@ -23,8 +23,8 @@ struct dfb_handle {
 
     // host-path plumbing: three streams so H2D of frame i+1, compute of pair i and D2H of flow i-1 overlap
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
-    static constexpr int kFrameRing = 4;  // device u8 frames (dead as soon as their pyramid is built)
-    static constexpr int kFlowRing = 3;   // device flow / quantised outputs
+    static constexpr int kFrameRing = 16; // device u8 frames (dead as soon as their pyramid is built)
+    static constexpr int kFlowRing = 16;  // device flow / quantised outputs (two launches of up to 8 pairs in flight)
     uint8_t *d_frame[kFrameRing] = {};
     size_t d_frame_pitch = 0;
     float *d_flow[kFlowRing] = {};
@@ -116,7 +116,8 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
     if (M == 0) return DFB_OK;
     ensure_host_path(h);
     FlowAlgorithm &alg = *h->alg;
-    alg.ensure_slots(astep + 2);
+    const int Bpre = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), dfb_handle::kFlowRing / 2));
+    alg.ensure_slots(Bpre + astep + 1);
     const int nslots = alg.num_slots();
     const size_t fbytes = (size_t)w * hh;
     constexpr int FR = dfb_handle::kFrameRing, OR = dfb_handle::kFlowRing;
@@ -156,37 +157,55 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
         pending_copy[ring] = -1;
     };
 
-    for (int j = 0; j < M; ++j) {
-        const int a = step > 0 ? j : j + astep;  // :315
-        const int b = step > 0 ? j + astep : j;  // :316
-        upload_until(std::min(std::max(a, b) + 1, n_frames - 1));  // one frame ahead: its H2D overlaps this solve
-        const int ring = j % OR;
-        drain(ring);
-        if (j >= OR) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_out[ring], 0));  // device output slot is free
-        alg.solve(a % nslots, b % nslots, w, hh, h->d_flow[ring], (size_t)w * 2 * sizeof(float), h->s_compute);
-        if (bound > 0) {
-            launch_quantise(h->d_flow[ring], (size_t)w * 2 * sizeof(float), w, hh, bound, h->d_qx[ring], h->d_qy[ring], w,
-                            h->s_compute);
-            ++alg.launches;
+    const int B = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), OR / 2));
+    alg.ensure_slots(B + astep + 1);
+    const int nslots2 = alg.num_slots();
+    (void)nslots;
+    std::vector<FlowAlgorithm::PairJob> jobs(B);
+    for (int j0 = 0; j0 < M; j0 += B) {
+        const int m = std::min(B, M - j0);
+        // frames of this group (+ one ahead, so its H2D overlaps the solve)
+        const int last_needed = step > 0 ? j0 + m - 1 + astep : j0 + m - 1 + astep;
+        upload_until(std::min(last_needed + 1, n_frames - 1));
+        for (int i = 0; i < m; ++i) {
+            const int j = j0 + i;
+            const int a = step > 0 ? j : j + astep;  // :315
+            const int b = step > 0 ? j + astep : j;  // :316
+            const int ring = j % OR;
+            drain(ring);
+            if (j >= OR) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_out[ring], 0));  // device output slot is free
+            jobs[i] = FlowAlgorithm::PairJob{a % nslots2, b % nslots2, h->d_flow[ring], (size_t)w * 2 * sizeof(float)};
         }
-        DFB_CUDA(cudaEventRecord(h->ev_done[ring], h->s_compute));
-        DFB_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[ring], 0));
-        if (bound > 0) {
-            const bool direct = is_pinned_or_device(qx[j]) && is_pinned_or_device(qy[j]);
-            uint8_t *dx = direct ? qx[j] : h->h_q[ring], *dy = direct ? qy[j] : h->h_q[ring] + fbytes;
-            DFB_CUDA(cudaMemcpyAsync(dx, h->d_qx[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
-            DFB_CUDA(cudaMemcpyAsync(dy, h->d_qy[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
-            if (!direct) pending_copy[ring] = j;
-            h->counters.d2h_bytes += 2 * fbytes;
-        } else {
-            const bool direct = is_pinned_or_device(flows[j]);
-            DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : h->h_flow[ring], h->d_flow[ring], fbytes * 2 * sizeof(float),
-                                     cudaMemcpyDeviceToHost, h->s_out));
-            if (!direct) pending_copy[ring] = j;
-            h->counters.d2h_bytes += fbytes * 2 * sizeof(float);
+        alg.solve_batch(jobs.data(), m, w, hh, h->s_compute);
+        for (int i = 0; i < m; ++i) {
+            const int j = j0 + i, ring = j % OR;
+            if (bound > 0) {
+                launch_quantise(h->d_flow[ring], (size_t)w * 2 * sizeof(float), w, hh, bound, h->d_qx[ring], h->d_qy[ring], w,
+                                h->s_compute);
+                ++alg.launches;
+            }
         }
-        DFB_CUDA(cudaEventRecord(h->ev_out[ring], h->s_out));
-        ++h->counters.pairs;  // total_flows += 1 (:340)
+        DFB_CUDA(cudaEventRecord(h->ev_done[j0 % OR], h->s_compute));
+        DFB_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[j0 % OR], 0));
+        for (int i = 0; i < m; ++i) {
+            const int j = j0 + i, ring = j % OR;
+            if (bound > 0) {
+                const bool direct = is_pinned_or_device(qx[j]) && is_pinned_or_device(qy[j]);
+                uint8_t *dx = direct ? qx[j] : h->h_q[ring], *dy = direct ? qy[j] : h->h_q[ring] + fbytes;
+                DFB_CUDA(cudaMemcpyAsync(dx, h->d_qx[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
+                DFB_CUDA(cudaMemcpyAsync(dy, h->d_qy[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
+                if (!direct) pending_copy[ring] = j;
+                h->counters.d2h_bytes += 2 * fbytes;
+            } else {
+                const bool direct = is_pinned_or_device(flows[j]);
+                DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : h->h_flow[ring], h->d_flow[ring], fbytes * 2 * sizeof(float),
+                                         cudaMemcpyDeviceToHost, h->s_out));
+                if (!direct) pending_copy[ring] = j;
+                h->counters.d2h_bytes += fbytes * 2 * sizeof(float);
+            }
+            DFB_CUDA(cudaEventRecord(h->ev_out[ring], h->s_out));
+            ++h->counters.pairs;  // total_flows += 1 (:340)
+        }
     }
     DFB_CUDA(cudaStreamSynchronize(h->s_out));
     for (int r = 0; r < OR; ++r) drain(r);
@@ -356,17 +375,24 @@ int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, in
         DFB_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         FlowAlgorithm &alg = *h->alg;
-        alg.ensure_slots(astep + 2);
+        const int B = std::max(1, alg.max_concurrent_pairs(width, height));
+        alg.ensure_slots(B + astep + 1);
         const int nslots = alg.num_slots();
         const size_t fbytes = (size_t)width * height;
         int prepared = 0;
-        for (int j = 0; j < M; ++j) {
-            const int a = step > 0 ? j : j + astep;
-            const int b = step > 0 ? j + astep : j;
-            for (; prepared <= std::max(a, b); ++prepared)
+        std::vector<FlowAlgorithm::PairJob> jobs(B);
+        for (int j0 = 0; j0 < M; j0 += B) {
+            const int m = std::min(B, M - j0);
+            for (; prepared <= j0 + m - 1 + astep; ++prepared)
                 alg.prepare_frame(frames + (size_t)prepared * fbytes, width, width, height, prepared % nslots, s);
-            alg.solve(a % nslots, b % nslots, width, height, flows + (size_t)j * fbytes * 2, (size_t)width * 8, s);
-            ++h->counters.pairs;
+            for (int i = 0; i < m; ++i) {
+                const int j = j0 + i;
+                const int a = step > 0 ? j : j + astep;
+                const int b = step > 0 ? j + astep : j;
+                jobs[i] = FlowAlgorithm::PairJob{a % nslots, b % nslots, flows + (size_t)j * fbytes * 2, (size_t)width * 8};
+            }
+            alg.solve_batch(jobs.data(), m, width, height, s);
+            h->counters.pairs += m;
         }
         return DFB_OK;
     });
@@ -404,6 +430,15 @@ int dfb_get_counters(dfb_handle *h, dfb_counters *out) {
         *out = h->counters;
         out->kernel_launches = h->alg->launches;
         out->pixel_iters = h->alg->pixel_iters;
+        return DFB_OK;
+    });
+}
+
+int dfb_get_tvl1_phase_ns(dfb_handle *h, uint64_t out[32]) {
+    if (!h || !out) return DFB_ERR_INVALID_ARG;
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        h->alg->phase_ns(out);
         return DFB_OK;
     });
 }

@@ -32,9 +32,20 @@ class FlowAlgorithm {
     // per-pair work: flow(slot_a -> slot_b) into interleaved float2 rows
     virtual void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes,
                        cudaStream_t s) = 0;
+    // several independent pairs at once (the fused tvl1 engine runs them side by side on disjoint SM groups)
+    struct PairJob {
+        int slot_a, slot_b;
+        float *flow_xy;
+        size_t flow_pitch_bytes;
+    };
+    virtual int max_concurrent_pairs(int w, int h) { (void)w; (void)h; return 1; }
+    virtual void solve_batch(const PairJob *jobs, int n, int w, int h, cudaStream_t s) {
+        for (int i = 0; i < n; ++i) solve(jobs[i].slot_a, jobs[i].slot_b, w, h, jobs[i].flow_xy, jobs[i].flow_pitch_bytes, s);
+    }
     virtual bool set_param(const std::string &name, double v) = 0;
     virtual bool get_param(const std::string &name, double *v) const = 0;
     virtual void tvl1_stats(dfb_tvl1_stats *out) { *out = dfb_tvl1_stats{}; }
+    virtual void phase_ns(uint64_t *out) { for (int i = 0; i < 32; ++i) out[i] = 0; }
     virtual void reset_counters() { launches = 0; pixel_iters = 0; }
     uint64_t launches = 0;     // kernels launched
     uint64_t pixel_iters = 0;  // tvl1: sum of level pixels over executed inner iterations

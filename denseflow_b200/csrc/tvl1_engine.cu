@@ -31,6 +31,8 @@ struct Tvl1Params {
     double scale_step = 0.8;
     int fused = 1;
     int fused_k = 8;
+    int flag_sync = 1;
+    int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
 class Tvl1 final : public FlowAlgorithm {
@@ -42,7 +44,11 @@ class Tvl1 final : public FlowAlgorithm {
     ~Tvl1() override {
         cudaSetDevice(device_);
         for (auto p : extra_slots_) cudaFree(p);
-        if (host_ctl_) cudaFreeHost(host_ctl_);
+        for (auto &l : lanes_) {
+            if (l.host_ctl) cudaFreeHost(l.host_ctl);
+            if (l.own) cudaFree(l.own);
+        }
+        if (stats_event_) cudaEventDestroy(stats_event_);
     }
     const char *name() const override { return "tvl1"; }
     int num_slots() const override { return (int)slots_.size(); }
@@ -67,6 +73,8 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "scale_step") { if (!(v > 0 && v < 1)) return false; prm_.scale_step = v; }
         else if (k == "fused") prm_.fused = v != 0;
         else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
+        else if (k == "flag_sync") prm_.flag_sync = v != 0;
+        else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
     }
@@ -81,6 +89,8 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "scale_step") *v = prm_.scale_step;
         else if (k == "fused") *v = prm_.fused;
         else if (k == "fused_k") *v = prm_.fused_k;
+        else if (k == "flag_sync") *v = prm_.flag_sync;
+        else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
     }
@@ -118,20 +128,73 @@ class Tvl1 final : public FlowAlgorithm {
         const int n = level_geometry(w, h, lv);
         last_nscales_ = n;
         std::memcpy(last_lv_, lv, sizeof(lv));
-        if (prm_.fused)
-            solve_fused(slot_a, slot_b, lv, n, flow_xy, flow_pitch_bytes, s);
-        else
+        if (prm_.fused) {
+            const PairJob one{slot_a, slot_b, flow_xy, flow_pitch_bytes};
+            solve_fused(&one, 1, lv, n, s);
+        } else {
             solve_unfused(slot_a, slot_b, lv, n, flow_xy, flow_pitch_bytes, s);
+        }
     }
 
+    // pairs per fused launch.  Utilisation model: a lane of G = SMs / B CTAs visits tiles(level) tiles
+    // in ceil(tiles / G) rounds; weight the levels by where the iterations are (the coarsest scale runs
+    // most of them), pick the B with the fewest idle CTA-rounds.
+    int max_concurrent_pairs(int w, int h) override {
+        if (!prm_.fused) return 1;
+        if (prm_.lanes > 0) return prm_.lanes;
+        LevelGeom lv[kMaxScales];
+        const int n = level_geometry(w, h, lv);
+        const int sms = fused_num_sms(device_);
+        const int hy = prm_.fused_k, hx = (hy + 3) & ~3;
+        int best = 1;
+        double best_u = -1;
+        for (int B = 1; B <= kFusedMaxLanes; ++B) {
+            const int G = sms / B;
+            if (G < 1) break;
+            double num = 0, den = 0;
+            for (int l = 0; l < n; ++l) {
+                const double wgt = l == n - 1 ? 7.0 : (l == n - 2 ? 1.5 : 1.0);
+                const int tiles = fused_tiles_along(lv[l].w, kFusedTileW, hx) * fused_tiles_along(lv[l].h, kFusedTileH, hy);
+                const int rounds = (tiles + G - 1) / G;
+                num += wgt * tiles;
+                den += wgt * (double)rounds * G;
+            }
+            const double u = num / den * (double)(G * B) / sms;
+            if (u > best_u + 0.02) {
+                best_u = u;
+                best = B;
+            }
+        }
+        return best;
+    }
+
+    void solve_batch(const PairJob *jobs, int count, int w, int h, cudaStream_t s) override {
+        LevelGeom lv[kMaxScales];
+        const int n = level_geometry(w, h, lv);
+        last_nscales_ = n;
+        std::memcpy(last_lv_, lv, sizeof(lv));
+        if (!prm_.fused) {
+            for (int i = 0; i < count; ++i)
+                solve_unfused(jobs[i].slot_a, jobs[i].slot_b, lv, n, jobs[i].flow_xy, jobs[i].flow_pitch_bytes, s);
+            return;
+        }
+        const int B = std::min(max_concurrent_pairs(w, h), kFusedMaxLanes);
+        for (int i = 0; i < count; i += B) solve_fused(jobs + i, std::min(B, count - i), lv, n, s);
+    }
+
+    void phase_ns(uint64_t *out) override {
+        if (stats_pending_) DFB_CUDA(cudaEventSynchronize(stats_event_));
+        for (int i = 0; i < 32; ++i) out[i] = prm_.fused ? lanes_[last_lane_].host_ctl->prof[i] : 0;
+    }
     void tvl1_stats(dfb_tvl1_stats *out) override {
         *out = dfb_tvl1_stats{};
         if (stats_pending_) {  // fused engine: the log was written by the kernel into mapped host memory
             DFB_CUDA(cudaEventSynchronize(stats_event_));
-            for (int i = 0; i < 16 * 16; ++i) last_iters_[i] = host_ctl_->iters[i];
+            for (int i = 0; i < 16 * 16; ++i) last_iters_[i] = lanes_[last_lane_].host_ctl->iters[i];
             stats_pending_ = false;
         }
-        pixel_iters = unfused_px_iters_ + host_ctl_->px_iters_total;
+        pixel_iters = unfused_px_iters_;
+        for (auto &l : lanes_) pixel_iters += l.host_ctl->px_iters_total;
         out->nscales = last_nscales_;
         out->warps = prm_.warps;
         for (int s = 0; s < last_nscales_; ++s) {
@@ -166,34 +229,54 @@ class Tvl1 final : public FlowAlgorithm {
         }
         plane_elems_ = (size_t)lv[0].pitch * (lv[0].h + 1);
         constexpr int kInitialSlots = 4;
-        const int n_work = 2 /*I1x,I1y*/ + 4 /*consts*/ + 12 /*u,p ping-pong*/;
-        size_t bytes = 0;
-        bytes += kInitialSlots * Slab::padded(pyr_elems_, 4);
-        bytes += 2 * 2 * Slab::padded(pyr_elems_, 4);  // u1s,u2s pyramids, two buffers each
-        bytes += n_work * Slab::padded(plane_elems_, 4);
-        bytes += Slab::padded(kMaxPartials, 8) + Slab::padded(64, 8) + (1 << 16);
-        slab_.reserve(bytes);
+        slab_.reserve(kInitialSlots * Slab::padded(pyr_elems_, 4) + (1 << 12));
         for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(pyr_elems_));
-        for (int b = 0; b < 2; ++b) {
-            u1pyr_[b] = slab_.take<float>(pyr_elems_);
-            u2pyr_[b] = slab_.take<float>(pyr_elems_);
-        }
-        I1x_ = slab_.take<float>(plane_elems_);
-        I1y_ = slab_.take<float>(plane_elems_);
-        I1wx_ = slab_.take<float>(plane_elems_);
-        I1wy_ = slab_.take<float>(plane_elems_);
-        grad_ = slab_.take<float>(plane_elems_);
-        rho_c_ = slab_.take<float>(plane_elems_);
-        for (int b = 0; b < 2; ++b)
-            for (int k = 0; k < 4; ++k) p_[b][k] = slab_.take<float>(plane_elems_);
-        partials_ = slab_.take<double>(kMaxPartials);
-        sync_words_ = slab_.take<unsigned>(64);
-        DFB_CUDA(cudaHostAlloc(&host_ctl_, sizeof(FusedHostCtl), cudaHostAllocMapped));
-        std::memset(host_ctl_, 0, sizeof(FusedHostCtl));
-        DFB_CUDA(cudaHostGetDevicePointer(&dev_ctl_, host_ctl_, 0));
+        ensure_lanes(1);
         DFB_CUDA(cudaEventCreateWithFlags(&stats_event_, cudaEventDisableTiming));
         // every plane starts finite: padding columns are read (never used) by vectorised kernels
         slab_.zero();
+    }
+
+    // per-pair workspace: flow pyramids (ping-pong), gradient / warp planes, dual variables (ping-pong),
+    // convergence partials, barrier words and the mapped control block
+    struct Lane {
+        void *own = nullptr;
+        float *u1pyr[2] = {}, *u2pyr[2] = {};
+        float *I1x = nullptr, *I1y = nullptr, *I1wx = nullptr, *I1wy = nullptr, *grad = nullptr, *rho_c = nullptr;
+        float *p[2][4] = {};
+        double *partials = nullptr;
+        unsigned *sync = nullptr;
+        FusedHostCtl *host_ctl = nullptr, *dev_ctl = nullptr;
+    };
+
+    void ensure_lanes(int n) {
+        while ((int)lanes_.size() < n) {
+            Lane l;
+            const size_t pyr = Slab::padded(pyr_elems_, 4), pl = Slab::padded(plane_elems_, 4);
+            const size_t bytes = 4 * pyr + 14 * pl + Slab::padded(kMaxPartials, 8) + 256;
+            DFB_CUDA(cudaMalloc(&l.own, bytes));
+            DFB_CUDA(cudaMemset(l.own, 0, bytes));  // planes start finite: padding is read (never used) by vector loads
+            char *c = static_cast<char *>(l.own);
+            auto take = [&](size_t b) { char *r = c; c += b; return r; };
+            for (int b = 0; b < 2; ++b) {
+                l.u1pyr[b] = reinterpret_cast<float *>(take(pyr));
+                l.u2pyr[b] = reinterpret_cast<float *>(take(pyr));
+            }
+            l.I1x = reinterpret_cast<float *>(take(pl));
+            l.I1y = reinterpret_cast<float *>(take(pl));
+            l.I1wx = reinterpret_cast<float *>(take(pl));
+            l.I1wy = reinterpret_cast<float *>(take(pl));
+            l.grad = reinterpret_cast<float *>(take(pl));
+            l.rho_c = reinterpret_cast<float *>(take(pl));
+            for (int b = 0; b < 2; ++b)
+                for (int k = 0; k < 4; ++k) l.p[b][k] = reinterpret_cast<float *>(take(pl));
+            l.partials = reinterpret_cast<double *>(take(Slab::padded(kMaxPartials, 8)));
+            l.sync = reinterpret_cast<unsigned *>(take(256));
+            DFB_CUDA(cudaHostAlloc(&l.host_ctl, sizeof(FusedHostCtl), cudaHostAllocMapped));
+            std::memset(l.host_ctl, 0, sizeof(FusedHostCtl));
+            DFB_CUDA(cudaHostGetDevicePointer(&l.dev_ctl, l.host_ctl, 0));
+            lanes_.push_back(l);
+        }
     }
 
     Plane work(float *p, const LevelGeom &g) const { return Plane{p, g.w, g.h, g.pitch}; }
@@ -203,14 +286,15 @@ class Tvl1 final : public FlowAlgorithm {
                        cudaStream_t s) {
         const Tvl1Consts c{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
         std::memset(last_iters_, 0, sizeof(last_iters_));
+        Lane &wk = lanes_[0];
         float *I0b = slots_.at(slot_a), *I1b = slots_.at(slot_b);
         for (int l = n - 1; l >= 0; --l) {
             const LevelGeom &g = lv[l];
             const Plane I0 = level_plane(I0b, lv, l), I1 = level_plane(I1b, lv, l);
-            const Plane u1 = level_plane(u1pyr_[0], lv, l), u2 = level_plane(u2pyr_[0], lv, l);
-            const Plane I1x = work(I1x_, g), I1y = work(I1y_, g), I1wx = work(I1wx_, g), I1wy = work(I1wy_, g);
-            const Plane grad = work(grad_, g), rho_c = work(rho_c_, g);
-            const Plane p11 = work(p_[0][0], g), p12 = work(p_[0][1], g), p21 = work(p_[0][2], g), p22 = work(p_[0][3], g);
+            const Plane u1 = level_plane(wk.u1pyr[0], lv, l), u2 = level_plane(wk.u2pyr[0], lv, l);
+            const Plane I1x = work(wk.I1x, g), I1y = work(wk.I1y, g), I1wx = work(wk.I1wx, g), I1wy = work(wk.I1wy, g);
+            const Plane grad = work(wk.grad, g), rho_c = work(wk.rho_c, g);
+            const Plane p11 = work(wk.p[0][0], g), p12 = work(wk.p[0][1], g), p21 = work(wk.p[0][2], g), p22 = work(wk.p[0][3], g);
             if (l == n - 1) {  // useInitialFlow = false
                 launch_fill(u1, 0.f, s);
                 launch_fill(u2, 0.f, s);
@@ -232,13 +316,13 @@ class Tvl1 final : public FlowAlgorithm {
                 for (; error > scaled_eps && it < prm_.iterations; ++it) {
                     const bool calc_error = prm_.epsilon > 0 && (it & 1) && prev_error < scaled_eps;
                     launch_estimate_u(I1wx, I1wy, grad, rho_c, p11, p12, p21, p22, u1, u2, c,
-                                      calc_error ? partials_ : nullptr, s);
+                                      calc_error ? wk.partials : nullptr, s);
                     ++launches;
                     if (calc_error) {
-                        launch_sum_partials(partials_, nblk, &dev_ctl_->error, s);
+                        launch_sum_partials(wk.partials, nblk, &wk.dev_ctl->error, s);
                         ++launches;
                         DFB_CUDA(cudaStreamSynchronize(s));  // the reference syncs here too (stream.waitForCompletion)
-                        error = host_ctl_->error;
+                        error = wk.host_ctl->error;
                         prev_error = error;
                     } else {
                         error = DBL_MAX;
@@ -253,58 +337,70 @@ class Tvl1 final : public FlowAlgorithm {
                 const float ufx = (float)(1.0 / ((double)lv[l - 1].w / (double)g.w));
                 const float ufy = (float)(1.0 / ((double)lv[l - 1].h / (double)g.h));
                 const float mul = (float)(1.0 / prm_.scale_step);
-                launch_resize_linear(u1, level_plane(u1pyr_[0], lv, l - 1), ufx, ufy, mul, s);
-                launch_resize_linear(u2, level_plane(u2pyr_[0], lv, l - 1), ufx, ufy, mul, s);
+                launch_resize_linear(u1, level_plane(wk.u1pyr[0], lv, l - 1), ufx, ufy, mul, s);
+                launch_resize_linear(u2, level_plane(wk.u2pyr[0], lv, l - 1), ufx, ufy, mul, s);
                 launches += 2;
             }
         }
-        launch_merge_flow(level_plane(u1pyr_[0], lv, 0), level_plane(u2pyr_[0], lv, 0), flow_xy, flow_pitch_bytes, s);
+        launch_merge_flow(level_plane(wk.u1pyr[0], lv, 0), level_plane(wk.u2pyr[0], lv, 0), flow_xy, flow_pitch_bytes, s);
         ++launches;
         stats_pending_ = false;
         accumulate_pixel_iters();
     }
 
     // ---- fused = 1 -------------------------------------------------------------------------------
-    void solve_fused(int slot_a, int slot_b, const LevelGeom *lv, int n, float *flow_xy, size_t flow_pitch_bytes,
-                     cudaStream_t s) {
-        FusedJob job{};
-        job.nscales = n;
-        job.warps = prm_.warps;
-        job.iterations = prm_.iterations;
-        job.epsilon = prm_.epsilon;
-        job.k = prm_.fused_k;
-        job.c = Tvl1Consts{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
-        job.up_mul = (float)(1.0 / prm_.scale_step);
-        for (int l = 0; l < n; ++l) {
-            FusedLevel &L = job.lv[l];
-            L.w = lv[l].w;
-            L.h = lv[l].h;
-            L.pitch = lv[l].pitch;
-            L.I0 = level_plane(slots_.at(slot_a), lv, l).p;
-            L.I1 = level_plane(slots_.at(slot_b), lv, l).p;
-            for (int b = 0; b < 2; ++b) {
-                L.u1[b] = level_plane(u1pyr_[b], lv, l).p;
-                L.u2[b] = level_plane(u2pyr_[b], lv, l).p;
+    void solve_fused(const PairJob *jobs, int count, const LevelGeom *lv, int n, cudaStream_t s) {
+        ensure_lanes(count);
+        FusedBatch batch{};
+        batch.njobs = count;
+        batch.group = std::max(1, fused_num_sms(device_) / count);
+        for (int i = 0; i < count; ++i) {
+            Lane &wk = lanes_[i];
+            FusedJob &job = batch.job[i];
+            job.nscales = n;
+            job.warps = prm_.warps;
+            job.iterations = prm_.iterations;
+            job.epsilon = prm_.epsilon;
+            job.k = prm_.fused_k;
+            job.flag_sync = prm_.flag_sync;
+            job.c = Tvl1Consts{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
+            job.up_mul = (float)(1.0 / prm_.scale_step);
+            for (int l = 0; l < n; ++l) {
+                FusedLevel &L = job.lv[l];
+                L.w = lv[l].w;
+                L.h = lv[l].h;
+                L.pitch = lv[l].pitch;
+                L.I0 = level_plane(slots_.at(jobs[i].slot_a), lv, l).p;
+                L.I1 = level_plane(slots_.at(jobs[i].slot_b), lv, l).p;
+                for (int b = 0; b < 2; ++b) {
+                    L.u1[b] = level_plane(wk.u1pyr[b], lv, l).p;
+                    L.u2[b] = level_plane(wk.u2pyr[b], lv, l).p;
+                }
+                if (l > 0) {
+                    L.up_fx = (float)(1.0 / ((double)lv[l - 1].w / (double)lv[l].w));
+                    L.up_fy = (float)(1.0 / ((double)lv[l - 1].h / (double)lv[l].h));
+                }
             }
-            if (l > 0) {
-                L.up_fx = (float)(1.0 / ((double)lv[l - 1].w / (double)lv[l].w));
-                L.up_fy = (float)(1.0 / ((double)lv[l - 1].h / (double)lv[l].h));
-            }
+            job.I1x = wk.I1x;
+            job.I1y = wk.I1y;
+            job.I1wx = wk.I1wx;
+            job.I1wy = wk.I1wy;
+            job.grad = wk.grad;
+            job.rho_c = wk.rho_c;
+            for (int b = 0; b < 2; ++b)
+                for (int k = 0; k < 4; ++k) job.p[b][k] = wk.p[b][k];
+            job.partials = wk.partials;
+            job.sync = wk.sync;
+            job.ctl = wk.dev_ctl;
+            job.flow_xy = jobs[i].flow_xy;
+            job.flow_pitch_bytes = jobs[i].flow_pitch_bytes;
         }
-        job.I1x = I1x_;
-        job.I1y = I1y_;
-        job.I1wx = I1wx_;
-        job.I1wy = I1wy_;
-        job.grad = grad_;
-        job.rho_c = rho_c_;
-        for (int b = 0; b < 2; ++b)
-            for (int k = 0; k < 4; ++k) job.p[b][k] = p_[b][k];
-        job.partials = partials_;
-        job.sync = sync_words_;
-        job.ctl = dev_ctl_;
-        job.flow_xy = flow_xy;
-        job.flow_pitch_bytes = flow_pitch_bytes;
-        launches += launch_tvl1_fused(job, device_, s);
+        // one CTA per SM at most: the tile counts of the largest level bound the useful group size
+        const int hx = 4, hy = 1;
+        const int max_tiles = fused_tiles_along(lv[0].w, kFusedTileW, hx) * fused_tiles_along(lv[0].h, kFusedTileH, hy);
+        batch.group = std::max(1, std::min(batch.group, max_tiles));
+        launches += launch_tvl1_fused(batch, device_, s);
+        last_lane_ = count - 1;
         DFB_CUDA(cudaEventRecord(stats_event_, s));
         stats_pending_ = true;
     }
@@ -322,7 +418,7 @@ class Tvl1 final : public FlowAlgorithm {
         launches = 0;
         pixel_iters = 0;
         unfused_px_iters_ = 0;
-        host_ctl_->px_iters_total = 0;
+        for (auto &l : lanes_) l.host_ctl->px_iters_total = 0;
     }
     uint64_t unfused_px_iters_ = 0;
 
@@ -335,12 +431,8 @@ class Tvl1 final : public FlowAlgorithm {
     std::vector<float *> extra_slots_;
     size_t max_lv_elems_[kMaxScales] = {};
     size_t pyr_elems_ = 0, plane_elems_ = 0;
-    float *u1pyr_[2] = {}, *u2pyr_[2] = {};
-    float *I1x_ = nullptr, *I1y_ = nullptr, *I1wx_ = nullptr, *I1wy_ = nullptr, *grad_ = nullptr, *rho_c_ = nullptr;
-    float *p_[2][4] = {};
-    double *partials_ = nullptr;
-    unsigned *sync_words_ = nullptr;
-    FusedHostCtl *host_ctl_ = nullptr, *dev_ctl_ = nullptr;
+    std::vector<Lane> lanes_;
+    int last_lane_ = 0;
     cudaEvent_t stats_event_ = nullptr;
     bool stats_pending_ = false;
     int last_nscales_ = 0;

@@ -45,20 +45,29 @@ struct Smem {
     double red[kWarps];
     double bcast[4];
     int ibcast[4];
+    unsigned long long prof[32];
+    int prog[kWarps];  // per-warp progress counters of the tile loop (see process_tile)
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- grid barrier ---------------------------------------------------------------------------
-// sync[0] counts arrivals monotonically: barrier number b completes when it reaches b * gridDim.x.
+// sync[0] counts arrivals monotonically: barrier number b of a lane completes when it reaches b * G
+// (G = CTAs in the lane's group).
 // bar.sync orders the CTA's writes before thread 0's gpu-scope fence + atomic (release); the
 // fence after the spin makes other CTAs' writes visible and invalidates this SM's L1.
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch) {
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch, int G) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        epoch += gridDim.x;
+        epoch += G;
         __threadfence();
         atomicAdd(counter, 1u);
         unsigned v;
@@ -71,10 +80,10 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch)
 }
 
 // ---- pixel-parallel phases (grid-stride over the level) --------------------------------------
-__device__ __forceinline__ void phase_level_start(const FusedJob &job, const FusedLevel &L, bool coarsest) {
+__device__ __forceinline__ void phase_level_start(const int G, const int bid, const FusedJob &job, const FusedLevel &L, bool coarsest) {
     const int W = L.w, H = L.h, P = L.pitch;
     const int total = H * (P >> 2);
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int y = i / (P >> 2), x0 = (i - y * (P >> 2)) << 2;
         const size_t o = (size_t)y * P + x0;
         // A.2 step 2: p = 0 once per scale; A.2: u = 0 at the coarsest scale
@@ -105,27 +114,42 @@ __device__ __forceinline__ void phase_level_start(const FusedJob &job, const Fus
 }
 
 // A.2 "Warp (warpBackward)" for the whole level: reads u[cur], writes the four per-warp constants.
-__device__ __forceinline__ void phase_warp(const FusedJob &job, const FusedLevel &L, int cur) {
+// The reference sums taps cx = ceil(wx-2) .. floor(wx+2) (4, or 5 when wx is integral, in which case
+// both end taps have weight k(+-2) = 0).  Anchored at xmin = ceil(wx-2) the distance to tap xmin+4 is
+// in [2,3), so its weight is always exactly 0: a fixed 4x4 window with separable weights gives the
+// same sums (tap order preserved: rows outer, columns inner).
+__device__ __forceinline__ void phase_warp(const int G, const int bid, const FusedJob &job, const FusedLevel &L, int cur) {
     const int W = L.w, H = L.h, P = L.pitch;
     const float *u1 = L.u1[cur], *u2 = L.u2[cur];
+    const float *__restrict__ I1 = L.I1;
+    const float *I1x = job.I1x, *I1y = job.I1y;  // written before the last grid barrier (which invalidated L1)
     const int total = H * W;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int y = i / W, x = i - y * W;
         const size_t o = (size_t)y * P + x;
-        const float u1v = __ldcg(u1 + o), u2v = __ldcg(u2 + o);
+        const float u1v = u1[o], u2v = u2[o];
         const float wx = x + u1v, wy = y + u2v;
-        const int xmin = (int)ceilf(wx - 2.0f), xmax = (int)floorf(wx + 2.0f);
-        const int ymin = (int)ceilf(wy - 2.0f), ymax = (int)floorf(wy + 2.0f);
+        const int xmin = (int)ceilf(wx - 2.0f), ymin = (int)ceilf(wy - 2.0f);
+        float kx[4], ky[4];
+        int cxs[4];
+        size_t rows[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            kx[t] = bicubic_coeff(wx - (float)(xmin + t));
+            ky[t] = bicubic_coeff(wy - (float)(ymin + t));
+            cxs[t] = max(0, min(xmin + t, W - 1));
+            rows[t] = (size_t)max(0, min(ymin + t, H - 1)) * P;
+        }
         float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
-        for (int cy = ymin; cy <= ymax; ++cy) {
-            const float wyc = bicubic_coeff(wy - cy);
-            const size_t ro = (size_t)max(0, min(cy, H - 1)) * P;
-            for (int cx = xmin; cx <= xmax; ++cx) {
-                const float wgt = bicubic_coeff(wx - cx) * wyc;
-                const size_t t = ro + max(0, min(cx, W - 1));
-                sum = sum + wgt * __ldg(L.I1 + t);
-                sumx = sumx + wgt * __ldcg(job.I1x + t);
-                sumy = sumy + wgt * __ldcg(job.I1y + t);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float wgt = kx[b] * ky[a];
+                const size_t t = rows[a] + cxs[b];
+                sum = sum + wgt * __ldg(I1 + t);
+                sumx = sumx + wgt * I1x[t];
+                sumy = sumy + wgt * I1y[t];
                 wsum = wsum + wgt;
             }
         }
@@ -139,9 +163,9 @@ __device__ __forceinline__ void phase_warp(const FusedJob &job, const FusedLevel
 }
 
 // A.2 step 4: upsample this level's flow to the next finer level (explicit dsize), x float(1/scaleStep)
-__device__ __forceinline__ void phase_upsample(const FusedJob &job, const FusedLevel &L, const FusedLevel &F, int cur) {
+__device__ __forceinline__ void phase_upsample(const int G, const int bid, const FusedJob &job, const FusedLevel &L, const FusedLevel &F, int cur) {
     const int total = F.h * F.w;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int dy = i / F.w, dx = i - dy * F.w;
         const float sx = dx * L.up_fx, sy = dy * L.up_fy;
         const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
@@ -166,9 +190,9 @@ __device__ __forceinline__ void phase_upsample(const FusedJob &job, const FusedL
 }
 
 // A.5: merge(u1,u2) -> CV_32FC2
-__device__ __forceinline__ void phase_merge(const FusedJob &job, const FusedLevel &L, int cur) {
+__device__ __forceinline__ void phase_merge(const int G, const int bid, const FusedJob &job, const FusedLevel &L, int cur) {
     const int total = L.h * L.w;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int y = i / L.w, x = i - y * L.w;
         const size_t o = (size_t)y * L.pitch + x;
         float2 *row = reinterpret_cast<float2 *>(reinterpret_cast<char *>(job.flow_xy) + (size_t)y * job.flow_pitch_bytes);
@@ -177,58 +201,104 @@ __device__ __forceinline__ void phase_merge(const FusedJob &job, const FusedLeve
 }
 
 // ---- the register-tile inner loop -------------------------------------------------------------
-// Runs kk primal+dual iterations on the tile whose region origin is (rx0, ry0) (image coords, may be
-// negative), reading state from buffers [cur] and writing the interior (region shrunk by hx / hy) to
-// [cur^1].  Returns this thread's share of sum(diff) of the last primal step when `check`.
-__device__ __forceinline__ double process_tile(const FusedJob &job, const FusedLevel &L, int cur, int rx0, int ry0,
-                                               int kk, int hx, int hy, bool check, Smem &sm) {
+// Tile (tx, ty) has its region origin at (tx*iw, ty*ih) (image coordinates, never negative), where
+// iw = TW - 2hx, ih = TH - 2hy.  After kk <= min(hx, hy) iterations a pixel is valid unless it lies
+// within the halo of a region edge that is NOT an image border: the first tile row/column keeps its
+// top/left margin (the region edge is the image edge, where p(-1) = 0 is exactly the zero a region
+// edge supplies), later tiles start their interior hx / hy in; the right/bottom margins are clipped
+// by the image.  Reads state [cur], writes the interior to [cur^1].
+//
+// Warps synchronise only with their vertical neighbours, through progress counters in shared
+// memory (sm.prog): warp q publishes row 0 of its new u after each primal step and row RPT-1 of its
+// new p12/p22 after each dual step; the primal step of iteration i waits for warp q-1 to have
+// finished dual(i-1), the dual step for warp q+1 to have finished primal(i).  Warps therefore drift
+// apart by up to one half-step per row block, which overlaps the MUFU-heavy dual phase of some
+// warps with the FMA-heavy primal phase of others, and no CTA-wide barrier sits in the loop.
+// `base` is the counter value that means "tile loaded"; it advances by 2*kk + 2 per tile.
+//
+// Index-clamped forward differences (u(x+1) = u(x) on the last column / row): the pixel just outside
+// the image is overwritten with a copy of the border pixel after every primal step, so the
+// difference is exactly 0 without per-pixel masking; only tiles touching that border pay for it.
+// Returns this thread's share of sum(diff) of the last primal step when `check`.
+__device__ __forceinline__ void wait_ge(const volatile int *flag, int v) {
+    while (*flag - v < 0) {
+    }
+}
+__device__ __forceinline__ void signal(volatile int *flag, int v) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        *flag = v;
+    }
+}
+
+__device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLevel &L, int cur, int tx, int ty, int kk,
+                                           int hx, int hy, bool check, int base, Smem &sm, bool prof_on) {
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    unsigned long long t0 = 0;
+    if (prof_on) t0 = gtime();
     const int W = L.w, H = L.h, P = L.pitch;
+    const int rx0 = tx * (TW - 2 * hx), ry0 = ty * (TH - 2 * hy);
     const int gx0 = rx0 + 4 * lane;
     const int gy0 = ry0 + RPT * wq;
-    const Tvl1Consts c = job.c;
+    const float l_t = job.c.l_t, taut = job.c.taut, theta = job.c.theta;
+    volatile int *prog = sm.prog;
+    const bool flagsync = job.flag_sync != 0;  // 0: CTA-wide barriers between half-steps (debug / comparison)
 
-    const float *src[6] = {L.u1[cur], L.u2[cur], job.p[cur][0], job.p[cur][1], job.p[cur][2], job.p[cur][3]};
     float4 u1[RPT], u2[RPT], p11[RPT], p12[RPT], p21[RPT], p22[RPT];
-    const bool col_ok = gx0 >= 0 && gx0 < P;
+    {
+        const float *s0 = L.u1[cur], *s1 = L.u2[cur], *s2 = job.p[cur][0], *s3 = job.p[cur][1], *s4 = job.p[cur][2],
+                    *s5 = job.p[cur][3];
+        const bool col_ok = gx0 < P;
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int gy = gy0 + r;
-        const bool ok = col_ok && gy >= 0 && gy < H;
-        const size_t o = ok ? (size_t)gy * P + gx0 : 0;
-        u1[r] = ok ? ld_cg4(src[0] + o) : zero4();
-        u2[r] = ok ? ld_cg4(src[1] + o) : zero4();
-        p11[r] = ok ? ld_cg4(src[2] + o) : zero4();
-        p12[r] = ok ? ld_cg4(src[3] + o) : zero4();
-        p21[r] = ok ? ld_cg4(src[4] + o) : zero4();
-        p22[r] = ok ? ld_cg4(src[5] + o) : zero4();
-        const int so = (RPT * wq + r) * TW + 4 * lane;
-        st4(&sm.consts[0][so], ok ? ld_cg4(job.I1wx + o) : zero4());
-        st4(&sm.consts[1][so], ok ? ld_cg4(job.I1wy + o) : zero4());
-        st4(&sm.consts[2][so], ok ? ld_cg4(job.grad + o) : zero4());
-        st4(&sm.consts[3][so], ok ? ld_cg4(job.rho_c + o) : zero4());
+        for (int r = 0; r < RPT; ++r) {
+            const int gy = gy0 + r;
+            const bool ok = col_ok && gy < H;
+            const size_t o = ok ? (size_t)gy * P + gx0 : 0;
+            u1[r] = ok ? ld_cg4(s0 + o) : zero4();
+            u2[r] = ok ? ld_cg4(s1 + o) : zero4();
+            p11[r] = ok ? ld_cg4(s2 + o) : zero4();
+            p12[r] = ok ? ld_cg4(s3 + o) : zero4();
+            p21[r] = ok ? ld_cg4(s4 + o) : zero4();
+            p22[r] = ok ? ld_cg4(s5 + o) : zero4();
+            const int so = (RPT * wq + r) * TW + 4 * lane;
+            st4(&sm.consts[0][so], ok ? ld_cg4(job.I1wx + o) : zero4());
+            st4(&sm.consts[1][so], ok ? ld_cg4(job.I1wy + o) : zero4());
+            st4(&sm.consts[2][so], ok ? ld_cg4(job.grad + o) : zero4());
+            st4(&sm.consts[3][so], ok ? ld_cg4(job.rho_c + o) : zero4());
+        }
     }
-    // border flags (image coordinates).  gx0 is a multiple of 4, so x == 0 can only be lane-pixel 0.
-    const bool left_edge = gx0 == 0;
-    const int jlast = W - 1 - gx0;  // pixel j == jlast is the last image column (forward diff clamps)
-    bool top_edge[RPT], bot_edge[RPT];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        top_edge[r] = gy0 + r == 0;
-        bot_edge[r] = gy0 + r == H - 1;
-    }
+    // image borders inside this tile's region (tile-uniform)
+    const bool edge_x = W - 1 >= rx0 && W - 1 < rx0 + TW;
+    const bool edge_y = H - 1 >= ry0 && H - 1 < ry0 + TH;
+    const int jlast = W - 1 - gx0;  // pixel j == jlast of this lane is the last image column
+    const int rbot = H - 1 - gy0;   // row r == rbot of this warp is the last image row
+    // which of this thread's pixels are interior (written back / counted in the error)
+    const bool lane_in = (tx == 0 || 4 * lane >= hx) && 4 * lane < TW - hx + (rx0 + TW >= W ? hx : 0) && gx0 < W;
+    const int ry_lo = ty == 0 ? 0 : hy, ry_hi = TH - hy + (ry0 + TH >= H ? hy : 0);
 
-    // make row 3 of p12/p22 visible to the warp below before the first primal step
+    // make row RPT-1 of p12/p22 visible to the warp below before the first primal step
     st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
     st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-    __syncthreads();
+    signal(&prog[wq], base);
+    if (!flagsync) __syncthreads();
+    if (prof_on) {
+        const unsigned long long t = gtime();
+        sm.prof[5] += t - t0;
+        t0 = t;
+    }
 
-    double err = 0.0;
+    float err = 0.f;
     for (int it = 0; it < kk; ++it) {
         const bool do_err = check && it == kk - 1;
         // -------- primal: u <- u + d(rho) + theta * div p --------------------------------------
-        float4 up12 = wq > 0 ? *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]) : zero4();
-        float4 up22 = wq > 0 ? *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]) : zero4();
+        // p above the region's first row: the image border (p = 0) for tile row 0, halo garbage otherwise
+        float4 up12 = zero4(), up22 = zero4();
+        if (wq > 0) {
+            if (flagsync) wait_ge(&prog[wq - 1], base + 2 * it);
+            up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
+            up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
+        }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int so = (RPT * wq + r) * TW + 4 * lane;
@@ -238,87 +308,117 @@ __device__ __forceinline__ double process_tile(const FusedJob &job, const FusedL
             const float4 rc = *reinterpret_cast<const float4 *>(&sm.consts[3][so]);
             float l11 = __shfl_up_sync(0xffffffffu, p11[r].w, 1);
             float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
-            if (left_edge || lane == 0) l11 = l21 = 0.f;  // p outside the image is 0 (lane 0: region edge, halo)
-            if (top_edge[r]) up12 = up22 = zero4();
+            if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
             float4 n1, n2;
-            tvl1_primal_px(ix.x, iy.x, g.x, rc.x, u1[r].x, u2[r].x, (p11[r].x - l11) + (p12[r].x - up12.x), (p21[r].x - l21) + (p22[r].x - up22.x), c, n1.x, n2.x);
-            tvl1_primal_px(ix.y, iy.y, g.y, rc.y, u1[r].y, u2[r].y, (p11[r].y - p11[r].x) + (p12[r].y - up12.y), (p21[r].y - p21[r].x) + (p22[r].y - up22.y), c, n1.y, n2.y);
-            tvl1_primal_px(ix.z, iy.z, g.z, rc.z, u1[r].z, u2[r].z, (p11[r].z - p11[r].y) + (p12[r].z - up12.z), (p21[r].z - p21[r].y) + (p22[r].z - up22.z), c, n1.z, n2.z);
-            tvl1_primal_px(ix.w, iy.w, g.w, rc.w, u1[r].w, u2[r].w, (p11[r].w - p11[r].z) + (p12[r].w - up12.w), (p21[r].w - p21[r].z) + (p22[r].w - up22.w), c, n1.w, n2.w);
+#define DFB_PRIMAL(C, PL11, PL21)                                                                      \
+    {                                                                                                  \
+        const float rho = rc.C + (ix.C * u1[r].C + iy.C * u2[r].C);                                    \
+        const float thr = l_t * g.C;                                                                   \
+        float f = g.C > FLT_EPSILON ? f_div(-rho, g.C) : 0.f;                                          \
+        f = rho > thr ? -l_t : f;                                                                      \
+        f = rho < -thr ? l_t : f;                                                                      \
+        const float d1 = f * ix.C, d2 = f * iy.C;                                                      \
+        const float div1 = (p11[r].C - (PL11)) + (p12[r].C - up12.C);                                  \
+        const float div2 = (p21[r].C - (PL21)) + (p22[r].C - up22.C);                                  \
+        n1.C = (u1[r].C + d1) + theta * div1;                                                          \
+        n2.C = (u2[r].C + d2) + theta * div2;                                                          \
+    }
+            DFB_PRIMAL(x, l11, l21)
+            DFB_PRIMAL(y, p11[r].x, p21[r].x)
+            DFB_PRIMAL(z, p11[r].y, p21[r].y)
+            DFB_PRIMAL(w, p11[r].z, p21[r].z)
+#undef DFB_PRIMAL
             if (do_err) {
-                // interior pixels inside the image only: every pixel is counted by exactly one tile
-                const int ry = RPT * wq + r, gy = gy0 + r;
-                const bool row_in = ry >= hy && ry < TH - hy && gy < H;
-                const bool lane_in = 4 * lane >= hx && 4 * lane < TW - hx;
-                if (row_in && lane_in) {
-                    float d;
-                    if (gx0 + 0 < W) { d = (u1[r].x - n1.x) * (u1[r].x - n1.x) + (u2[r].x - n2.x) * (u2[r].x - n2.x); err += (double)d; }
-                    if (gx0 + 1 < W) { d = (u1[r].y - n1.y) * (u1[r].y - n1.y) + (u2[r].y - n2.y) * (u2[r].y - n2.y); err += (double)d; }
-                    if (gx0 + 2 < W) { d = (u1[r].z - n1.z) * (u1[r].z - n1.z) + (u2[r].z - n2.z) * (u2[r].z - n2.z); err += (double)d; }
-                    if (gx0 + 3 < W) { d = (u1[r].w - n1.w) * (u1[r].w - n1.w) + (u2[r].w - n2.w) * (u2[r].w - n2.w); err += (double)d; }
+                const int ry = RPT * wq + r;
+                if (lane_in && ry >= ry_lo && ry < ry_hi && gy0 + r < H) {
+                    // diff = (u1-u1')^2 + (u2-u2')^2 per pixel (fp32, as the reference's diff plane)
+                    err += (u1[r].x - n1.x) * (u1[r].x - n1.x) + (u2[r].x - n2.x) * (u2[r].x - n2.x);
+                    if (gx0 + 1 < W) err += (u1[r].y - n1.y) * (u1[r].y - n1.y) + (u2[r].y - n2.y) * (u2[r].y - n2.y);
+                    if (gx0 + 2 < W) err += (u1[r].z - n1.z) * (u1[r].z - n1.z) + (u2[r].z - n2.z) * (u2[r].z - n2.z);
+                    if (gx0 + 3 < W) err += (u1[r].w - n1.w) * (u1[r].w - n1.w) + (u2[r].w - n2.w) * (u2[r].w - n2.w);
                 }
+            }
+            if (edge_x) {  // mirror the last image column into the pixel right of it: u(x+1) - u(x) == 0 there
+                if (jlast == 0) { n1.y = n1.x; n2.y = n2.x; }
+                if (jlast == 1) { n1.z = n1.y; n2.z = n2.y; }
+                if (jlast == 2) { n1.w = n1.z; n2.w = n2.z; }
             }
             u1[r] = n1;
             u2[r] = n2;
             up12 = p12[r];
             up22 = p22[r];
         }
+        if (edge_y) {  // mirror the last image row into the row below it
+#pragma unroll
+            for (int r = 0; r < RPT - 1; ++r)
+                if (r == rbot) {
+                    u1[r + 1] = u1[r];
+                    u2[r + 1] = u2[r];
+                }
+        }
         st4(&sm.u_top[0][wq][4 * lane], u1[0]);
         st4(&sm.u_top[1][wq][4 * lane], u2[0]);
-        __syncthreads();
+        signal(&prog[wq], base + 2 * it + 1);
+        if (!flagsync) __syncthreads();
         // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ------------------------
+        float4 dn1 = u1[RPT - 1], dn2 = u2[RPT - 1];  // region's last row: halo, or mirrored image border
+        if (wq < kWarps - 1) {
+            if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1);
+            if (!(edge_y && rbot == RPT - 1)) {
+                dn1 = *reinterpret_cast<const float4 *>(&sm.u_top[0][wq + 1][4 * lane]);
+                dn2 = *reinterpret_cast<const float4 *>(&sm.u_top[1][wq + 1][4 * lane]);
+            }
+        }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            float4 d1, d2;
-            if (r < RPT - 1) {
-                d1 = u1[r + 1];
-                d2 = u2[r + 1];
-            } else if (wq < kWarps - 1) {
-                d1 = *reinterpret_cast<const float4 *>(&sm.u_top[0][wq + 1][4 * lane]);
-                d2 = *reinterpret_cast<const float4 *>(&sm.u_top[1][wq + 1][4 * lane]);
-            } else {
-                d1 = u1[r];
-                d2 = u2[r];
+            const float4 d1 = r < RPT - 1 ? u1[r + 1] : dn1;
+            const float4 d2 = r < RPT - 1 ? u2[r + 1] : dn2;
+            float r1 = __shfl_down_sync(0xffffffffu, u1[r].x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, u2[r].x, 1);
+            if (edge_x && jlast == 3) {
+                r1 = u1[r].w;
+                r2 = u2[r].w;
             }
-            if (bot_edge[r]) {  // u(y+1) = u(y) on the last image row
-                d1 = u1[r];
-                d2 = u2[r];
-            }
-            const float r1 = __shfl_down_sync(0xffffffffu, u1[r].x, 1);
-            const float r2 = __shfl_down_sync(0xffffffffu, u2[r].x, 1);
-            // u(x+1) - u(x), zero on the last image column
-            const float e1 = jlast == 0 ? 0.f : u1[r].y - u1[r].x, e2 = jlast == 0 ? 0.f : u2[r].y - u2[r].x;
-            const float f1 = jlast == 1 ? 0.f : u1[r].z - u1[r].y, f2 = jlast == 1 ? 0.f : u2[r].z - u2[r].y;
-            const float g1 = jlast == 2 ? 0.f : u1[r].w - u1[r].z, g2 = jlast == 2 ? 0.f : u2[r].w - u2[r].z;
-            const float h1 = jlast == 3 ? 0.f : r1 - u1[r].w, h2 = jlast == 3 ? 0.f : r2 - u2[r].w;
-            tvl1_dual_px(e1, d1.x - u1[r].x, e2, d2.x - u2[r].x, c.taut, p11[r].x, p12[r].x, p21[r].x, p22[r].x);
-            tvl1_dual_px(f1, d1.y - u1[r].y, f2, d2.y - u2[r].y, c.taut, p11[r].y, p12[r].y, p21[r].y, p22[r].y);
-            tvl1_dual_px(g1, d1.z - u1[r].z, g2, d2.z - u2[r].z, c.taut, p11[r].z, p12[r].z, p21[r].z, p22[r].z);
-            tvl1_dual_px(h1, d1.w - u1[r].w, h2, d2.w - u2[r].w, c.taut, p11[r].w, p12[r].w, p21[r].w, p22[r].w);
+            tvl1_dual_px(u1[r].y - u1[r].x, d1.x - u1[r].x, u2[r].y - u2[r].x, d2.x - u2[r].x, taut, p11[r].x, p12[r].x, p21[r].x, p22[r].x);
+            tvl1_dual_px(u1[r].z - u1[r].y, d1.y - u1[r].y, u2[r].z - u2[r].y, d2.y - u2[r].y, taut, p11[r].y, p12[r].y, p21[r].y, p22[r].y);
+            tvl1_dual_px(u1[r].w - u1[r].z, d1.z - u1[r].z, u2[r].w - u2[r].z, d2.z - u2[r].z, taut, p11[r].z, p12[r].z, p21[r].z, p22[r].z);
+            tvl1_dual_px(r1 - u1[r].w, d1.w - u1[r].w, r2 - u2[r].w, d2.w - u2[r].w, taut, p11[r].w, p12[r].w, p21[r].w, p22[r].w);
         }
         st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
         st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-        __syncthreads();
+        signal(&prog[wq], base + 2 * it + 2);
+        if (!flagsync) __syncthreads();
     }
-
+    if (prof_on) {
+        const unsigned long long t = gtime();
+        sm.prof[6] += t - t0;
+        t0 = t;
+    }
     // -------- write the interior to the other buffer ---------------------------------------------
-    float *dst[6] = {L.u1[cur ^ 1], L.u2[cur ^ 1], job.p[cur ^ 1][0], job.p[cur ^ 1][1], job.p[cur ^ 1][2], job.p[cur ^ 1][3]};
-    const bool lane_in = 4 * lane >= hx && 4 * lane < TW - hx && gx0 < W;
+    {
+        float *d0 = L.u1[cur ^ 1], *d1 = L.u2[cur ^ 1], *d2 = job.p[cur ^ 1][0], *d3 = job.p[cur ^ 1][1],
+              *d4 = job.p[cur ^ 1][2], *d5 = job.p[cur ^ 1][3];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int ry = RPT * wq + r, gy = gy0 + r;
-        if (lane_in && ry >= hy && ry < TH - hy && gy < H) {
-            const size_t o = (size_t)gy * P + gx0;
-            st4(dst[0] + o, u1[r]);
-            st4(dst[1] + o, u2[r]);
-            st4(dst[2] + o, p11[r]);
-            st4(dst[3] + o, p12[r]);
-            st4(dst[4] + o, p21[r]);
-            st4(dst[5] + o, p22[r]);
+        for (int r = 0; r < RPT; ++r) {
+            const int ry = RPT * wq + r, gy = gy0 + r;
+            if (lane_in && ry >= ry_lo && ry < ry_hi && gy < H) {
+                const size_t o = (size_t)gy * P + gx0;
+                st4(d0 + o, u1[r]);
+                st4(d1 + o, u2[r]);
+                st4(d2 + o, p11[r]);
+                st4(d3 + o, p12[r]);
+                st4(d4 + o, p21[r]);
+                st4(d5 + o, p22[r]);
+            }
         }
     }
+    if (prof_on) sm.prof[7] += gtime() - t0;
     return err;
 }
+
+// tiles needed along one axis: tile i covers up to i*(T-2h) + T (clipped by the image) minus a halo that
+// only matters when the image continues beyond the region
+__host__ __device__ __forceinline__ int tiles_along(int n, int T, int h) { return fused_tiles_along(n, T, h); }
 
 __device__ __forceinline__ double block_sum(double v, Smem &sm) {
 #pragma unroll
@@ -334,23 +434,58 @@ __device__ __forceinline__ double block_sum(double v, Smem &sm) {
     return s;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant__ FusedJob job) {
+// phase profiler (CTA 0 / thread 0 only): attributes wall time between marks to a category
+struct Prof {
+    unsigned long long *acc;  // shared memory
+    unsigned long long last;
+    bool on;
+    __device__ void init(unsigned long long *a, bool first_cta) {
+        acc = a;
+        on = first_cta && threadIdx.x == 0;
+        if (on) {
+            for (int i = 0; i < 32; ++i) acc[i] = 0;
+            last = gtime();
+        }
+    }
+    __device__ __forceinline__ void mark(int cat, int cat2 = -1) {
+        if (on) {
+            const unsigned long long t = gtime();
+            acc[cat] += t - last;
+            if (cat2 >= 0) acc[cat2] += t - last;
+            last = t;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant__ FusedBatch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int G = batch.group;
+    const int lane_id = blockIdx.x / G, bid = blockIdx.x - lane_id * G;
+    const FusedJob &job = batch.job[lane_id];
     unsigned epoch = 0;
     unsigned *bar = job.sync;
     int cur = 0;
     unsigned long long px_iters = 0;
+    int tile_base = 1;  // progress-counter epoch of the tile loop (sm.prog starts at 0)
+    Prof prof;
+    prof.init(sm.prof, bid == 0);
+    if (threadIdx.x < kWarps) sm.prog[threadIdx.x] = 0;
+    __syncthreads();
 
     for (int s = job.nscales - 1; s >= 0; --s) {
         const FusedLevel &L = job.lv[s];
         cur = 0;  // level start: u[0] holds the upsampled (or zero) flow, p[0] is zeroed
-        phase_level_start(job, L, s == job.nscales - 1);
-        grid_barrier(bar, epoch);
+        phase_level_start(G, bid, job, L, s == job.nscales - 1);
+        prof.mark(0);
+        grid_barrier(bar, epoch, G);
+        prof.mark(3);
         const double scaled_eps = job.epsilon * job.epsilon * (double)((long long)L.w * L.h);  // A.4
         for (int wi = 0; wi < job.warps; ++wi) {
-            phase_warp(job, L, cur);
-            grid_barrier(bar, epoch);
+            phase_warp(G, bid, job, L, cur);
+            prof.mark(1);
+            grid_barrier(bar, epoch, G);
+            prof.mark(3);
             double error = DBL_MAX, prev_error = 0.0;
             int n = 0;
             while (error > scaled_eps && n < job.iterations) {
@@ -376,19 +511,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     const int kk = (remaining + nch - 1) / nch;
                     const bool chk = check && kk == remaining;
                     const int hx = (kk + 3) & ~3, hy = kk;
-                    const int iw = TW - 2 * hx, ih = TH - 2 * hy;
-                    const int ntx = (L.w + iw - 1) / iw, nty = (L.h + ih - 1) / ih;
+                    const int ntx = tiles_along(L.w, TW, hx), nty = tiles_along(L.h, TH, hy);
                     const int ntiles = ntx * nty;
-                    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                    for (int t = bid; t < ntiles; t += G) {
                         const int ty = t / ntx, tx = t - ty * ntx;
-                        const double e = process_tile(job, L, cur, tx * iw - hx, ty * ih - hy, kk, hx, hy, chk, sm);
+                        const float e = process_tile(job, L, cur, tx, ty, kk, hx, hy, chk, tile_base, sm, prof.on);
+                        tile_base += 2 * kk + 2;
                         if (chk) {
-                            const double bs = block_sum(e, sm);
+                            const double bs = block_sum((double)e, sm);
                             if (threadIdx.x == 0) cta_err += bs;
                         }
                     }
-                    if (chk && threadIdx.x == 0) job.partials[blockIdx.x] = cta_err;
-                    grid_barrier(bar, epoch);
+                    if (chk && threadIdx.x == 0) job.partials[bid] = cta_err;
+                    prof.mark(2, 8 + s);
+                    if (prof.on) prof.acc[16 + s] += 1;
+                    grid_barrier(bar, epoch, G);
+                    prof.mark(3);
                     cur ^= 1;
                     remaining -= kk;
                 }
@@ -397,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     // every CTA sums all partials in the same fixed order -> identical decisions everywhere
                     if (threadIdx.x < 32) {
                         double v = 0.0;
-                        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) v += __ldcg(job.partials + i);
+                        for (int i = threadIdx.x; i < G; i += 32) v += __ldcg(job.partials + i);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                         if (threadIdx.x == 0) sm.bcast[0] = v;
@@ -411,23 +549,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     prev_error = pp;
                 }
             }
-            if (blockIdx.x == 0 && threadIdx.x == 0) job.ctl->iters[s * job.warps + wi] = n;
+            if (bid == 0 && threadIdx.x == 0) job.ctl->iters[s * job.warps + wi] = n;
             px_iters += (unsigned long long)n * (unsigned long long)(L.w * L.h);
         }
         if (s > 0) {
-            phase_upsample(job, L, job.lv[s - 1], cur);
-            grid_barrier(bar, epoch);
+            phase_upsample(G, bid, job, L, job.lv[s - 1], cur);
+            prof.mark(4);
+            grid_barrier(bar, epoch, G);
+            prof.mark(3);
         }
     }
-    phase_merge(job, job.lv[0], cur);
-    if (blockIdx.x == 0 && threadIdx.x == 0) job.ctl->px_iters_total += px_iters;  // single writer, launches are serialised
+    phase_merge(G, bid, job, job.lv[0], cur);
+    prof.mark(4);
+    if (prof.on)
+        for (int i = 0; i < 32; ++i) job.ctl->prof[i] = prof.acc[i];
+    if (bid == 0 && threadIdx.x == 0) job.ctl->px_iters_total += px_iters;  // single writer, launches are serialised
 
     // last CTA out resets the barrier words for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned done = atomicAdd(bar + 1, 1u);
-        if (done == gridDim.x - 1) {
+        if (done == (unsigned)G - 1) {
             bar[0] = 0;
             bar[1] = 0;
             __threadfence();
@@ -437,22 +580,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
 
 }  // namespace
 
-int launch_tvl1_fused(const FusedJob &job, int device, cudaStream_t s) {
+int fused_num_sms(int device) {
     static int num_sms[64] = {};
+    if (device < 0 || device >= 64) return 148;
+    if (num_sms[device] == 0) DFB_CUDA(cudaDeviceGetAttribute(&num_sms[device], cudaDevAttrMultiProcessorCount, device));
+    return num_sms[device];
+}
+
+int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         configured = true;
     }
-    if (device < 64 && num_sms[device] == 0)
-        DFB_CUDA(cudaDeviceGetAttribute(&num_sms[device], cudaDevAttrMultiProcessorCount, device));
-    const int sms = device < 64 ? num_sms[device] : 148;
-    // enough CTAs for the busiest phase, never more than are co-resident (1 CTA / SM)
-    const FusedLevel &L0 = job.lv[0];
-    const int iw = TW - 8, ih = TH - 4;  // smallest halo => most tiles
-    const int max_tiles = ceil_div(L0.w, iw) * ceil_div(L0.h, ih);
-    const int grid = std::max(1, std::min(sms, max_tiles));
-    void *args[] = {const_cast<FusedJob *>(&job)};
+    static_assert(TW == kFusedTileW && TH == kFusedTileH, "tile geometry is shared with the host heuristics");
+    // all CTAs must be co-resident (1 CTA / SM): group * njobs <= SM count, enforced by the cooperative launch
+    const int grid = batch.group * batch.njobs;
+    void *args[] = {const_cast<FusedBatch *>(&batch)};
     DFB_CUDA(cudaLaunchCooperativeKernel((const void *)k_tvl1_pair, dim3(grid), dim3(kThreads), args, sizeof(Smem), s));
     return 1;
 }

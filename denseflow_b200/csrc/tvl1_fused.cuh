@@ -20,10 +20,14 @@ struct FusedHostCtl {
     double error;         // unfused engine: convergence sum read by the host state machine
     int iters[16 * 16];   // executed inner iterations per (scale, warp) of the last pair
     unsigned long long px_iters_total;  // sum over pairs of (level pixels x executed iterations)
+    // CTA-0 view of where the last pair's time went, in ns (globaltimer): [0] level start, [1] warps,
+    // [2] tile compute, [3] grid barriers, [4] upsample+merge, [8+s] tile compute at scale s, [16+s] chunks at scale s
+    unsigned long long prof[32];
 };
 
 struct FusedJob {
     int nscales, warps, iterations, k;
+    int flag_sync;  // 1: neighbour-warp progress counters in the tile loop, 0: CTA-wide barriers
     double epsilon;
     Tvl1Consts c;
     float up_mul;
@@ -37,7 +41,24 @@ struct FusedJob {
     size_t flow_pitch_bytes;
 };
 
+// Several independent pairs ("lanes") per launch: lane i is solved by CTAs [i*group, (i+1)*group) with
+// their own barrier words, partials and workspace.  Coarse pyramid levels have fewer tiles than the
+// GPU has SMs; running pairs side by side keeps every SM busy without touching a pair's arithmetic.
+constexpr int kFusedMaxLanes = 8;
+struct FusedBatch {
+    int njobs, group;
+    FusedJob job[kFusedMaxLanes];
+};
+
+// tiles needed along one axis (see process_tile): region origins at multiples of T - 2h
+__host__ __device__ inline int fused_tiles_along(int n, int T, int h) {
+    const int stride = T - 2 * h;
+    return n <= T ? 1 : (n - 2 * h + stride - 1) / stride;
+}
+constexpr int kFusedTileW = 128, kFusedTileH = 64;
+
+int fused_num_sms(int device);
 // returns the number of kernels launched
-int launch_tvl1_fused(const FusedJob &job, int device, cudaStream_t s);
+int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s);
 
 }  // namespace dfb

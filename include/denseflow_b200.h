@@ -129,6 +129,15 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
 } dfb_counters;
 int dfb_get_counters(dfb_handle *h, dfb_counters *out);
+
+/*
+ * Where the most recent fused-tvl1 pair's device time went, in ns, as seen by CTA 0 of the persistent
+ * kernel (%globaltimer): [0] level start (gradients, zeroing) [1] warps [2] tile iterations
+ * [3] grid barriers (includes waiting for slower CTAs) [4] upsample + merge, [8+s] tile iterations at
+ * scale s, [16+s] tile visits (chunks) at scale s.  Zeros for other engines.  (The reference has only the
+ * wall-clock summary line, src/denseflow_gpu.cpp:492-496.)
+ */
+int dfb_get_tvl1_phase_ns(dfb_handle *h, uint64_t out[32]);
 int dfb_reset_counters(dfb_handle *h);
 
 #ifdef __cplusplus
