@@ -28,7 +28,8 @@ class Tvl1Stats(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("kernel_launches", C.c_uint64), ("pixel_iters", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("timed_kernel_launches", C.c_uint64),
+                ("timed_kernel_ns", C.c_uint64), ("timed_kernel_pairs", C.c_uint64)]
 
 
 # every symbol include/denseflow_b200.h declares, with its signature

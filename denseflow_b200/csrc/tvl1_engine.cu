@@ -32,6 +32,7 @@ struct Tvl1Params {
     int fused = 1;
     int fused_k = 8;
     int flag_sync = 1;
+    int time_kernels = 0;
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
@@ -74,6 +75,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "fused") prm_.fused = v != 0;
         else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
         else if (k == "flag_sync") prm_.flag_sync = v != 0;
+        else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -90,6 +92,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "fused") *v = prm_.fused;
         else if (k == "fused_k") *v = prm_.fused_k;
         else if (k == "flag_sync") *v = prm_.flag_sync;
+        else if (k == "time_kernels") *v = prm_.time_kernels;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -399,12 +402,43 @@ class Tvl1 final : public FlowAlgorithm {
         const int hx = 4, hy = 1;
         const int max_tiles = fused_tiles_along(lv[0].w, kFusedTileW, hx) * fused_tiles_along(lv[0].h, kFusedTileH, hy);
         batch.group = std::max(1, std::min(batch.group, max_tiles));
+        if (prm_.time_kernels) {
+            if (timing_used_ == kTimingRing) drain_timing();
+            if (!timing_ev_[0][0])
+                for (int i = 0; i < kTimingRing; ++i) {
+                    DFB_CUDA(cudaEventCreate(&timing_ev_[i][0]));
+                    DFB_CUDA(cudaEventCreate(&timing_ev_[i][1]));
+                }
+            DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][0], s));
+        }
         launches += launch_tvl1_fused(batch, device_, s);
+        if (prm_.time_kernels) {
+            DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][1], s));
+            ++timing_used_;
+            timed_pairs_ += count;
+        }
         last_lane_ = count - 1;
         DFB_CUDA(cudaEventRecord(stats_event_, s));
         stats_pending_ = true;
     }
 
+    // CUDA-event timing of the dominant kernel (events on the launching stream, drained lazily)
+    void drain_timing() {
+        for (int i = 0; i < timing_used_; ++i) {
+            DFB_CUDA(cudaEventSynchronize(timing_ev_[i][1]));
+            float ms = 0.f;
+            DFB_CUDA(cudaEventElapsedTime(&ms, timing_ev_[i][0], timing_ev_[i][1]));
+            timed_ns_ += (uint64_t)((double)ms * 1e6);
+            ++timed_launches_;
+        }
+        timing_used_ = 0;
+    }
+    void kernel_timing(uint64_t *launches_, uint64_t *ns, uint64_t *pairs) override {
+        drain_timing();
+        *launches_ = timed_launches_;
+        *ns = timed_ns_;
+        *pairs = timed_pairs_;
+    }
     void accumulate_pixel_iters() {
         for (int l = 0; l < last_nscales_; ++l)
             for (int wi = 0; wi < prm_.warps; ++wi)
@@ -418,6 +452,8 @@ class Tvl1 final : public FlowAlgorithm {
         launches = 0;
         pixel_iters = 0;
         unfused_px_iters_ = 0;
+        drain_timing();
+        timed_launches_ = timed_ns_ = timed_pairs_ = 0;
         for (auto &l : lanes_) l.host_ctl->px_iters_total = 0;
     }
     uint64_t unfused_px_iters_ = 0;
@@ -432,6 +468,10 @@ class Tvl1 final : public FlowAlgorithm {
     size_t max_lv_elems_[kMaxScales] = {};
     size_t pyr_elems_ = 0, plane_elems_ = 0;
     std::vector<Lane> lanes_;
+    static constexpr int kTimingRing = 256;
+    cudaEvent_t timing_ev_[kTimingRing][2] = {};
+    int timing_used_ = 0;
+    uint64_t timed_launches_ = 0, timed_ns_ = 0, timed_pairs_ = 0;
     int last_lane_ = 0;
     cudaEvent_t stats_event_ = nullptr;
     bool stats_pending_ = false;

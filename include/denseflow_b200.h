@@ -59,7 +59,8 @@ const char *dfb_last_error(const dfb_handle *h);
  * Algorithm hyper-parameters.  The reference never sets any (always create() defaults); these exist
  * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations"
  * "scale_step"; engine knobs: "fused" (1 = persistent fused primal+dual kernel [default], 0 = one
- * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile).
+ * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile),
+ * "lanes" (pairs solved side by side per launch, 0 = auto), "flag_sync", "time_kernels".
  */
 int dfb_set_param(dfb_handle *h, const char *name, double value);
 int dfb_get_param(const dfb_handle *h, const char *name, double *value);
@@ -127,6 +128,11 @@ typedef struct {
     uint64_t kernel_launches; /* CUDA kernels launched by this handle */
     uint64_t pixel_iters;    /* sum over executed inner iterations of level pixels (tvl1) */
     uint64_t h2d_bytes, d2h_bytes;
+    /* dominant-kernel timing, CUDA events on the launching stream around every launch of the fused tvl1
+     * pair kernel (enabled with dfb_set_param(h, "time_kernels", 1)): */
+    uint64_t timed_kernel_launches;
+    uint64_t timed_kernel_ns;
+    uint64_t timed_kernel_pairs;
 } dfb_counters;
 int dfb_get_counters(dfb_handle *h, dfb_counters *out);
 
