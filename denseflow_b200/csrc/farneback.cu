@@ -1,8 +1,502 @@
-// farneback.cu — Farneback path (placeholder until the kernels land).
+// farneback.cu — the Farneback path on sm_100a: what cv::cuda::FarnebackOpticalFlow::calc executes with
+// the argument-less create() defaults the reference uses (/root/reference/src/denseflow_gpu.cpp:301,329;
+// arithmetic per SURVEY.md Appendix B: numLevels 5, pyrScale .5, winSize 13, numIters 10, polyN 5,
+// polySigma 1.1, flags 0 = box filter).
+//
+// Per level (coarse -> fine): Gaussian blur of the FULL-resolution frame + bilinear resize to the level
+// (B.2), polynomial expansion (B.3), then 10 x [13x13 box mean of the five M planes -> per-pixel 2x2
+// solve -> rebuild M] (B.4, B.5).  All planes are fp32 with 128-byte-aligned rows; the five planes of
+// R / M are stored as five separate planes of one pitch (the reference stacks them in a 5H x W matrix).
+// These kernels are HBM-bound 2-D stencils: separable passes staged through shared-memory tiles,
+// float4 on the interior, index-clamp / reflect-101 border rules applied on image coordinates.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "engine.h"
+#include "tvl1.cuh"
 
 namespace dfb {
-std::unique_ptr<FlowAlgorithm> make_farneback(int, int, int) {
-    throw std::runtime_error("farn: kernels not built yet");
+
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxHalf = 32;  // largest Gaussian half-width (smoothSize 39 at level 5 -> half 19)
+
+struct FarnConsts {
+    float g[8], xg[8], xxg[8];  // polyN <= 7
+    float ig11, ig03, ig33, ig55;
+};
+
+struct Plane5 {
+    float *p[5];
+    int w, h, pitch;
+};
+
+__host__ __device__ inline int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
 }
+
+// ---- B.2 Gaussian blur, separable, BORDER_REFLECT_101; vertical pass first (upstream order) -------
+// One CTA computes a 32 x 32 output tile: stage (32 + 2*half) rows x 32 cols vertically filtered... the
+// vertical pass needs rows y-half..y+half of the source; the horizontal pass needs the vertically
+// filtered values at x-half..x+half.  So: vertical-filter a (32 + 2*half)-wide strip of 32 rows into
+// shared memory, then filter horizontally out of shared memory.
+struct GaussKernel {
+    float k[kMaxHalf + 1];
+    int half;
+};
+
+constexpr int GT = 32;  // tile edge
+
+__global__ void __launch_bounds__(256) k_gauss_blur(Plane src, Plane dst, const GaussKernel gk) {
+    extern __shared__ float smem[];  // [GT][GT + 2*half]
+    const int half = gk.half;
+    const int sw = GT + 2 * half;
+    const int x0 = blockIdx.x * GT, y0 = blockIdx.y * GT;
+    // vertical pass into shared memory
+    for (int i = threadIdx.x; i < GT * sw; i += blockDim.x) {
+        const int ty = i / sw, tx = i - ty * sw;
+        const int y = min(y0 + ty, src.h - 1);
+        const int x = reflect101(x0 + tx - half, src.w);
+        float acc = src.p[(size_t)y * src.pitch + x] * gk.k[0];
+        for (int j = 1; j <= half; ++j)
+            acc = acc + (src.p[(size_t)reflect101(y - j, src.h) * src.pitch + x] + src.p[(size_t)reflect101(y + j, src.h) * src.pitch + x]) * gk.k[j];
+        smem[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GT * GT; i += blockDim.x) {
+        const int ty = i / GT, tx = i - ty * GT;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= dst.w || y >= dst.h) continue;
+        const float *row = smem + ty * sw + tx + half;
+        float acc = row[0] * gk.k[0];
+        for (int j = 1; j <= half; ++j) acc = acc + (row[-j] + row[j]) * gk.k[j];
+        dst.p[(size_t)y * dst.pitch + x] = acc;
+    }
+}
+
+// ---- B.3 polynomial expansion (polyN = 5): vertical pass (t0,t1,t2) then horizontal, index-clamped ----
+constexpr int PT = 32;
+
+template <int N>
+__global__ void __launch_bounds__(256) k_poly_exp(Plane src, Plane5 R, const FarnConsts c) {
+    __shared__ float t0[PT][PT + 2 * N], t1[PT][PT + 2 * N], t2[PT][PT + 2 * N];
+    constexpr int sw = PT + 2 * N;
+    const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT;
+    for (int i = threadIdx.x; i < PT * sw; i += blockDim.x) {
+        const int ty = i / sw, tx = i - ty * sw;
+        const int y = min(y0 + ty, src.h - 1);
+        const int x = max(0, min(x0 + tx - N, src.w - 1));
+        float a0 = src.p[(size_t)y * src.pitch + x] * c.g[0], a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            const float s0 = src.p[(size_t)max(y - k, 0) * src.pitch + x];
+            const float s1 = src.p[(size_t)min(y + k, src.h - 1) * src.pitch + x];
+            a0 = a0 + c.g[k] * (s0 + s1);
+            a1 = a1 + c.xg[k] * (s1 - s0);
+            a2 = a2 + c.xxg[k] * (s0 + s1);
+        }
+        t0[ty][tx] = a0;
+        t1[ty][tx] = a1;
+        t2[ty][tx] = a2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PT * PT; i += blockDim.x) {
+        const int ty = i / PT, tx = i - ty * PT;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= src.w || y >= src.h) continue;
+        const float *r0 = &t0[ty][tx + N], *r1 = &t1[ty][tx + N], *r2 = &t2[ty][tx + N];
+        float b1 = c.g[0] * r0[0], b3 = c.g[0] * r1[0], b5 = c.g[0] * r2[0], b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            float s = r0[k] + r0[-k];
+            b1 = b1 + s * c.g[k];
+            b4 = b4 + s * c.xxg[k];
+            b2 = b2 + (r0[k] - r0[-k]) * c.xg[k];
+            s = r1[k] + r1[-k];
+            b3 = b3 + s * c.g[k];
+            b6 = b6 + (r1[k] - r1[-k]) * c.xg[k];
+            s = r2[k] + r2[-k];
+            b5 = b5 + s * c.g[k];
+        }
+        const size_t o = (size_t)y * R.pitch + x;
+        R.p[0][o] = b3 * c.ig11;
+        R.p[1][o] = b2 * c.ig11;
+        R.p[2][o] = b1 * c.ig03 + b5 * c.ig33;
+        R.p[3][o] = b1 * c.ig03 + b4 * c.ig33;
+        R.p[4][o] = b6 * c.ig55;
+    }
+}
+
+__constant__ float c_border[6] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f, 1.f};
+
+// ---- B.4 updateMatrices ------------------------------------------------------------------------------
+__device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, float dx, float dy, const Plane5 &R0,
+                                                   const Plane5 &R1, float m[5]) {
+    const size_t o = (size_t)y * pitch + x;
+    float fx = x + dx, fy = y + dy;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= x1;
+    fy -= y1;
+    float r2, r3, r4, r5, r6;
+    if (x1 >= 0 && y1 >= 0 && x1 < w - 1 && y1 < h - 1) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const size_t j = (size_t)y1 * pitch + x1;
+        r2 = a00 * R1.p[0][j] + a01 * R1.p[0][j + 1] + a10 * R1.p[0][j + pitch] + a11 * R1.p[0][j + pitch + 1];
+        r3 = a00 * R1.p[1][j] + a01 * R1.p[1][j + 1] + a10 * R1.p[1][j + pitch] + a11 * R1.p[1][j + pitch + 1];
+        r4 = a00 * R1.p[2][j] + a01 * R1.p[2][j + 1] + a10 * R1.p[2][j + pitch] + a11 * R1.p[2][j + pitch + 1];
+        r5 = a00 * R1.p[3][j] + a01 * R1.p[3][j + 1] + a10 * R1.p[3][j + pitch] + a11 * R1.p[3][j + pitch + 1];
+        r6 = a00 * R1.p[4][j] + a01 * R1.p[4][j + 1] + a10 * R1.p[4][j + pitch] + a11 * R1.p[4][j + pitch + 1];
+        r4 = (R0.p[2][o] + r4) * 0.5f;
+        r5 = (R0.p[3][o] + r5) * 0.5f;
+        r6 = (R0.p[4][o] + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = R0.p[2][o];
+        r5 = R0.p[3][o];
+        r6 = R0.p[4][o] * 0.5f;
+    }
+    r2 = (R0.p[0][o] - r2) * 0.5f;
+    r3 = (R0.p[1][o] - r3) * 0.5f;
+    r2 = r2 + (r4 * dy + r6 * dx);
+    r3 = r3 + (r6 * dy + r5 * dx);
+    const float scale = c_border[min(x, 5)] * c_border[min(y, 5)] * c_border[min(w - x - 1, 5)] * c_border[min(h - y - 1, 5)];
+    r2 *= scale;
+    r3 *= scale;
+    r4 *= scale;
+    r5 *= scale;
+    r6 *= scale;
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
+
+__global__ void __launch_bounds__(256) k_update_matrices(Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 M) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= M.w || y >= M.h) return;
+    const size_t o = (size_t)y * M.pitch + x;
+    float m[5];
+    update_matrices_px(x, y, M.w, M.h, M.pitch, fxp.p[o], fyp.p[o], R0, R1, m);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) M.p[k][o] = m[k];
+}
+
+// ---- B.5 fused iteration: 13x13 box mean of the 5 planes of M -> 2x2 solve -> (optionally) rebuild M ------
+// One CTA produces a 32 x 16 tile of flow: the (32+12) x (16+12) window of each M plane is summed
+// vertically into shared memory (index-clamped), then horizontally; the solve and the rebuild of M for
+// the next iteration happen in registers.  M is double-buffered across iterations (Mout != Min): the
+// window of a neighbouring tile must still see this iteration's M.
+constexpr int BW = 32, BH = 16;
+
+template <int HALF>
+__global__ void __launch_bounds__(BW *BH) k_box_solve_update(Plane5 Min, Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 Mout,
+                                                             int rebuild) {
+    constexpr int sw = BW + 2 * HALF;
+    __shared__ float vs[5][BH][sw];
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    const int w = Min.w, h = Min.h, pitch = Min.pitch;
+    const int tid = threadIdx.y * BW + threadIdx.x;
+    for (int i = tid; i < BH * sw; i += BW * BH) {
+        const int ty = i / sw, tx = i - ty * sw;
+        const int y = min(y0 + ty, h - 1);
+        const int x = max(0, min(x0 + tx - HALF, w - 1));
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float *s = Min.p[k];
+            float acc = s[(size_t)y * pitch + x];
+#pragma unroll
+            for (int j = 1; j <= HALF; ++j) acc = acc + (s[(size_t)max(y - j, 0) * pitch + x] + s[(size_t)min(y + j, h - 1) * pitch + x]);
+            vs[k][ty][tx] = acc;
+        }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    constexpr float area_inv = 1.f / (float)((1 + 2 * HALF) * (1 + 2 * HALF));
+    float b[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float *row = &vs[k][threadIdx.y][threadIdx.x + HALF];
+        float acc = row[0];
+#pragma unroll
+        for (int j = 1; j <= HALF; ++j) acc = acc + (row[-j] + row[j]);
+        b[k] = acc * area_inv;
+    }
+    // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
+    const float det_inv = f_rcp(b[0] * b[2] - b[1] * b[1] + 1e-3f);
+    const float nfx = (b[0] * b[4] - b[1] * b[3]) * det_inv;
+    const float nfy = (b[2] * b[3] - b[1] * b[4]) * det_inv;
+    const size_t o = (size_t)y * pitch + x;
+    fxp.p[o] = nfx;
+    fyp.p[o] = nfy;
+    if (rebuild) {
+        float m[5];
+        update_matrices_px(x, y, w, h, pitch, nfx, nfy, R0, R1, m);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) Mout.p[k][o] = m[k];
+    }
+}
+
+struct FarnParams {
+    int num_levels = 5;
+    double pyr_scale = 0.5;
+    int win_size = 13;
+    int num_iters = 10;
+    int poly_n = 5;
+    double poly_sigma = 1.1;
+};
+
+inline int cv_round(double v) { return (int)std::nearbyint(v); }
+
+void inv6(double a[6][6], double inv[6][6]) {
+    double m[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            m[i][j] = a[i][j];
+            m[i][j + 6] = i == j ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(m[r][c]) > std::fabs(m[piv][c])) piv = r;
+        if (piv != c)
+            for (int j = 0; j < 12; ++j) std::swap(m[c][j], m[piv][j]);
+        const double d = 1.0 / m[c][c];
+        for (int j = 0; j < 12; ++j) m[c][j] *= d;
+        for (int r = 0; r < 6; ++r)
+            if (r != c) {
+                const double f = m[r][c];
+                for (int j = 0; j < 12; ++j) m[r][j] -= f * m[c][j];
+            }
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) inv[i][j] = m[i][j + 6];
+}
+
+// B.3 constants (upstream prepareGaussian)
+FarnConsts poly_constants(int n, double sigma) {
+    FarnConsts c{};
+    float gb[17], xgb[17], xxgb[17];
+    float *g = gb + n, *xg = xgb + n, *xxg = xxgb + n;
+    if (sigma < 1.19209289550781250000e-7) sigma = n * 0.3;
+    double s = 0.;
+    for (int x = -n; x <= n; ++x) {
+        g[x] = (float)std::exp(-x * x / (2 * sigma * sigma));
+        s += g[x];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x] = (float)(g[x] * s);
+        xg[x] = (float)(x * g[x]);
+        xxg[x] = (float)(x * x * g[x]);
+    }
+    double G[6][6];
+    std::memset(G, 0, sizeof(G));
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            G[0][0] += g[y] * g[x];
+            G[1][1] += g[y] * g[x] * x * x;
+            G[3][3] += g[y] * g[x] * x * x * x * x;
+            G[5][5] += g[y] * g[x] * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    double invG[6][6];
+    inv6(G, invG);
+    c.ig11 = (float)invG[1][1];
+    c.ig03 = (float)invG[0][3];
+    c.ig33 = (float)invG[3][3];
+    c.ig55 = (float)invG[5][5];
+    for (int k = 0; k <= n; ++k) {
+        c.g[k] = g[k];
+        c.xg[k] = xg[k];
+        c.xxg[k] = xxg[k];
+    }
+    return c;
+}
+
+// cv::getGaussianKernel(ksize, sigma, CV_32F): fixed table for small odd ksize with sigma <= 0
+GaussKernel gaussian_kernel(int ksize, double sigma) {
+    GaussKernel gk{};
+    gk.half = ksize / 2;
+    static const float tab1[] = {1.f}, tab3[] = {0.25f, 0.5f, 0.25f}, tab5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    static const float tab7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+    const float *fixed = nullptr;
+    if (ksize % 2 == 1 && ksize <= 7 && sigma <= 0) fixed = ksize == 1 ? tab1 : ksize == 3 ? tab3 : ksize == 5 ? tab5 : tab7;
+    if (fixed) {
+        for (int i = 0; i <= gk.half; ++i) gk.k[i] = fixed[gk.half + i];
+        return gk;
+    }
+    const double sx = sigma > 0 ? sigma : ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    const double scale2x = -0.5 / (sx * sx);
+    std::vector<double> tmp(ksize);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) * 0.5;
+        tmp[i] = std::exp(scale2x * x * x);
+        sum += tmp[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i <= gk.half; ++i) gk.k[i] = (float)(tmp[gk.half + i] * sum);
+    return gk;
+}
+
+class Farneback final : public FlowAlgorithm {
+  public:
+    Farneback(int device, int max_w, int max_h) : device_(device), max_w_(max_w), max_h_(max_h) {
+        DFB_CUDA(cudaSetDevice(device_));
+        pitch0_ = round_up(max_w_, 32);
+        plane_elems_ = (size_t)pitch0_ * (max_h_ + 1);
+        // frames (fp32, per slot), work planes: blurred, level image, R0[5], R1[5], M[5] x2, flow x/y x2 (cur + prev level)
+        const int n_work = 2 + 10 + 10 + 4;
+        slab_.reserve((kInitialSlots + n_work) * Slab::padded(plane_elems_, 4) + (1 << 12));
+        for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(plane_elems_));
+        blurred_ = slab_.take<float>(plane_elems_);
+        img_ = slab_.take<float>(plane_elems_);
+        for (int k = 0; k < 5; ++k) R_[0][k] = slab_.take<float>(plane_elems_);
+        for (int k = 0; k < 5; ++k) R_[1][k] = slab_.take<float>(plane_elems_);
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < 5; ++k) M_[b][k] = slab_.take<float>(plane_elems_);
+        for (int b = 0; b < 2; ++b) {
+            fx_[b] = slab_.take<float>(plane_elems_);
+            fy_[b] = slab_.take<float>(plane_elems_);
+        }
+        slab_.zero();
+        DFB_CUDA(cudaFuncSetAttribute(k_gauss_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, GT * (GT + 2 * kMaxHalf) * 4));
+    }
+    ~Farneback() override {
+        cudaSetDevice(device_);
+        for (auto p : extra_slots_) cudaFree(p);
+    }
+    const char *name() const override { return "farn"; }
+    int num_slots() const override { return (int)slots_.size(); }
+    void ensure_slots(int n) override {
+        while ((int)slots_.size() < n) {
+            float *p = nullptr;
+            DFB_CUDA(cudaMalloc(&p, plane_elems_ * sizeof(float)));
+            extra_slots_.push_back(p);
+            slots_.push_back(p);
+        }
+    }
+    bool set_param(const std::string &k, double v) override {
+        if (k == "num_levels") { if (v < 0 || v > kMaxLevels - 1) return false; prm_.num_levels = (int)v; }
+        else if (k == "pyr_scale") { if (!(v > 0 && v < 1)) return false; prm_.pyr_scale = v; }
+        else if (k == "num_iters") { if (v < 1) return false; prm_.num_iters = (int)v; }
+        else if (k == "poly_sigma") prm_.poly_sigma = v;
+        else if (k == "win_size" || k == "poly_n") return (k == "win_size" ? v == 13 : v == 5);  // compiled-in stencils
+        else return false;
+        return true;
+    }
+    bool get_param(const std::string &k, double *v) const override {
+        if (k == "num_levels") *v = prm_.num_levels;
+        else if (k == "pyr_scale") *v = prm_.pyr_scale;
+        else if (k == "win_size") *v = prm_.win_size;
+        else if (k == "num_iters") *v = prm_.num_iters;
+        else if (k == "poly_n") *v = prm_.poly_n;
+        else if (k == "poly_sigma") *v = prm_.poly_sigma;
+        else return false;
+        return true;
+    }
+
+    // per-frame work: u8 -> fp32 (the pyramid depends on the level's blur of the FULL-res frame, B.2, so it is built in solve)
+    void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) override {
+        launch_u8_to_f32(src, pitch_bytes, Plane{slots_.at(slot), w, h, round_up(w, 32)}, s);
+        ++launches;
+    }
+
+    void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes, cudaStream_t s) override {
+        const FarnConsts pc = poly_constants(prm_.poly_n, prm_.poly_sigma);
+        // B.1 level list
+        int cropped = 0;
+        double scale = 1.0;
+        for (; cropped < prm_.num_levels; ++cropped) {
+            scale *= prm_.pyr_scale;
+            if (w * scale < 32 || h * scale < 32) break;
+        }
+        const int pitch_full = round_up(w, 32);
+        const Plane frame[2] = {Plane{slots_.at(slot_a), w, h, pitch_full}, Plane{slots_.at(slot_b), w, h, pitch_full}};
+        int cur = 0, pw = 0, ph = 0, ppitch = 0;
+        bool have_prev = false;
+        for (int k = cropped; k >= 0; --k) {
+            scale = 1.0;
+            for (int i = 0; i < k; ++i) scale *= prm_.pyr_scale;
+            const double sigma = (1. / scale - 1) * 0.5;
+            int smooth = cv_round(sigma * 5) | 1;
+            smooth = std::max(smooth, 3);
+            const int W = cv_round(w * scale), H = cv_round(h * scale), pitch = round_up(W, 32);
+            const Plane fx{fx_[cur], W, H, pitch}, fy{fy_[cur], W, H, pitch};
+            if (!have_prev) {
+                launch_fill(fx, 0.f, s);
+                launch_fill(fy, 0.f, s);
+                launches += 2;
+            } else {
+                const float rfx = (float)(1.0 / ((double)W / (double)pw)), rfy = (float)(1.0 / ((double)H / (double)ph));
+                const float mul = (float)(1.0 / prm_.pyr_scale);
+                launch_resize_linear(Plane{fx_[cur ^ 1], pw, ph, ppitch}, fx, rfx, rfy, mul, s);
+                launch_resize_linear(Plane{fy_[cur ^ 1], pw, ph, ppitch}, fy, rfx, rfy, mul, s);
+                launches += 2;
+            }
+            Plane5 R[2];
+            const GaussKernel gk = gaussian_kernel(smooth, sigma);
+            if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
+            for (int i = 0; i < 2; ++i) {
+                const Plane blurred{blurred_, w, h, pitch_full};
+                k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame[i], blurred, gk);
+                DFB_KERNEL_CHECK();
+                const Plane img{img_, W, H, pitch};
+                const float rfx = (float)(1.0 / ((double)W / (double)w)), rfy = (float)(1.0 / ((double)H / (double)h));
+                launch_resize_linear(blurred, img, rfx, rfy, 1.0f, s);
+                R[i] = Plane5{{R_[i][0], R_[i][1], R_[i][2], R_[i][3], R_[i][4]}, W, H, pitch};
+                k_poly_exp<5><<<dim3(ceil_div(W, PT), ceil_div(H, PT)), 256, 0, s>>>(img, R[i], pc);
+                DFB_KERNEL_CHECK();
+                launches += 3;
+            }
+            int mb = 0;
+            Plane5 M[2] = {Plane5{{M_[0][0], M_[0][1], M_[0][2], M_[0][3], M_[0][4]}, W, H, pitch},
+                           Plane5{{M_[1][0], M_[1][1], M_[1][2], M_[1][3], M_[1][4]}, W, H, pitch}};
+            k_update_matrices<<<dim3(ceil_div(W, 32), ceil_div(H, 8)), dim3(32, 8), 0, s>>>(fx, fy, R[0], R[1], M[mb]);
+            DFB_KERNEL_CHECK();
+            ++launches;
+            for (int it = 0; it < prm_.num_iters; ++it) {
+                const int rebuild = it < prm_.num_iters - 1;
+                k_box_solve_update<6><<<dim3(ceil_div(W, BW), ceil_div(H, BH)), dim3(BW, BH), 0, s>>>(M[mb], fx, fy, R[0], R[1], M[mb ^ 1], rebuild);
+                DFB_KERNEL_CHECK();
+                ++launches;
+                mb ^= 1;
+            }
+            have_prev = true;
+            pw = W;
+            ph = H;
+            ppitch = pitch;
+            cur ^= 1;
+        }
+        // last processed level is full resolution (k = 0): merge
+        launch_merge_flow(Plane{fx_[cur ^ 1], w, h, pitch_full}, Plane{fy_[cur ^ 1], w, h, pitch_full}, flow_xy, flow_pitch_bytes, s);
+        ++launches;
+    }
+
+  private:
+    static constexpr int kInitialSlots = 4;
+    int device_, max_w_, max_h_, pitch0_ = 0;
+    size_t plane_elems_ = 0;
+    FarnParams prm_;
+    Slab slab_;
+    std::vector<float *> slots_, extra_slots_;
+    float *blurred_ = nullptr, *img_ = nullptr;
+    float *R_[2][5] = {}, *M_[2][5] = {};
+    float *fx_[2] = {}, *fy_[2] = {};
+};
+
+}  // namespace
+
+std::unique_ptr<FlowAlgorithm> make_farneback(int device, int max_w, int max_h) {
+    return std::unique_ptr<FlowAlgorithm>(new Farneback(device, max_w, max_h));
+}
+
 }  // namespace dfb
