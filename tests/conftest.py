@@ -16,6 +16,8 @@ def pytest_configure(config):
 def oracle():
     from oracle import pyoracle
     pyoracle.lib()
+    # small test images: a few threads beat 64 (OpenMP fork/join per row loop)
+    pyoracle.lib().orc_set_num_threads(min(8, os.cpu_count() or 1))
     return pyoracle
 
 

@@ -31,8 +31,11 @@ def test_farneback_matches_oracle(oracle, shape, variant):
 
 def test_farneback_small_frame_level_cropping(oracle):
     """Fewer than 5 levels when W*0.5^k < 32."""
+    a, b, _ = synth.pair(96, 160, 2)
+    assert len(oracle.farn_levels(160, 96)) == 2  # 160x96 -> 80x48 kept, 40x24 dropped (24 < 32)
+    assert len(oracle.farn_levels(80, 48)) == 1
+    assert synth.aee(_engine(160, 96).calc(a, b), oracle.farn_calc(a, b)) <= AEE_TOL
     a, b, _ = synth.pair(48, 80, 2)
-    assert len(oracle.farn_levels(80, 48)) == 2
     assert synth.aee(_engine(80, 48).calc(a, b), oracle.farn_calc(a, b)) <= AEE_TOL
 
 
