@@ -121,6 +121,19 @@ def make_stream(W, H, n_frames, seed, rank):
     return synth.stream(H, W, n_frames, seed + 1000 * rank, phase=7.0 * rank)
 
 
+def usable_cores():
+    """Cores this process may really use: scheduler affinity capped by the cgroup CPU quota (containers report the
+    host's core count in os.cpu_count())."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def _cpu_worker(job):
     alg, a, b, threads = job
     from oracle import pyoracle as O
@@ -133,7 +146,7 @@ def cpu_port_throughput(alg, frames, n_pairs_per_proc, warm=True):
     """The CPU restatement on ALL host cores: the per-pair OpenMP loops stop scaling long before 64 threads, so the
     cores are split into P processes x T threads working on different pairs concurrently (aggregate pairs/s)."""
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     threads = min(8, cores)
     procs = max(1, cores // threads)
     n = len(frames) - 1
@@ -159,7 +172,7 @@ def run_reference(args, alg, W, H, seed, desc):
         return
     import multiprocessing as mp
     frames = make_stream(W, H, 9, seed, 0)
-    cores_all = os.cpu_count() or 1
+    cores_all = usable_cores()
     threads = min(8, cores_all)
     procs = max(1, cores_all // threads)
     cores = procs * threads

@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATHS = {
     "default": os.path.join(_HERE, "lib", "libdenseflow_b200.so"),
     "strict": os.path.join(_HERE, "lib", "libdenseflow_b200_strict.so"),
+    "t448": os.path.join(_HERE, "lib", "libdenseflow_b200_t448.so"),
+    "t384": os.path.join(_HERE, "lib", "libdenseflow_b200_t384.so"),
 }
 
 DFB_OK = 0

@@ -31,7 +31,10 @@ namespace dfb {
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef DFB_FUSED_THREADS
+#define DFB_FUSED_THREADS 512
+#endif
+constexpr int kThreads = DFB_FUSED_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int RPT = 4;            // rows per thread
 constexpr int TW = 128;           // tile width  = 32 lanes x 4 px
@@ -40,7 +43,8 @@ constexpr int kConstPlane = TW * TH;
 
 struct Smem {
     float consts[4][kConstPlane];  // I1wx, I1wy, grad, rho_c of the current tile (thread-private slots)
-    float u_top[2][kWarps][TW];    // row 0 of every warp's u1/u2 (read by the warp above as "down")
+    float u[2][kConstPlane];       // u1, u2 of the current tile: written by the owning thread in the primal step,
+                                   // read by the row above / the lane to the left in the dual step
     float p_bot[2][kWarps][TW];    // row 3 of every warp's p12/p22 (read by the warp below as "up")
     double red[kWarps];
     double bcast[4];
@@ -245,7 +249,11 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
     volatile int *prog = sm.prog;
     const bool flagsync = job.flag_sync != 0;  // 0: CTA-wide barriers between half-steps (debug / comparison)
 
-    float4 u1[RPT], u2[RPT], p11[RPT], p12[RPT], p21[RPT], p22[RPT];
+    float4 p11[RPT], p12[RPT], p21[RPT], p22[RPT];
+    const int so0 = (RPT * wq) * TW + 4 * lane;  // this thread's slot in row 0 of its warp (thread-private in smem planes)
+    // The warp above reads this warp's first u row in its dual steps: it must have finished the previous
+    // tile (its counter reached base - 2 = "last dual step of the previous tile done") before the row is overwritten.
+    if (flagsync && wq > 0) wait_ge(&prog[wq - 1], base - 2);
     {
         const float *s0 = L.u1[cur], *s1 = L.u2[cur], *s2 = job.p[cur][0], *s3 = job.p[cur][1], *s4 = job.p[cur][2],
                     *s5 = job.p[cur][3];
@@ -255,13 +263,13 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             const int gy = gy0 + r;
             const bool ok = col_ok && gy < H;
             const size_t o = ok ? (size_t)gy * P + gx0 : 0;
-            u1[r] = ok ? ld_cg4(s0 + o) : zero4();
-            u2[r] = ok ? ld_cg4(s1 + o) : zero4();
             p11[r] = ok ? ld_cg4(s2 + o) : zero4();
             p12[r] = ok ? ld_cg4(s3 + o) : zero4();
             p21[r] = ok ? ld_cg4(s4 + o) : zero4();
             p22[r] = ok ? ld_cg4(s5 + o) : zero4();
-            const int so = (RPT * wq + r) * TW + 4 * lane;
+            const int so = so0 + r * TW;
+            st4(&sm.u[0][so], ok ? ld_cg4(s0 + o) : zero4());
+            st4(&sm.u[1][so], ok ? ld_cg4(s1 + o) : zero4());
             st4(&sm.consts[0][so], ok ? ld_cg4(job.I1wx + o) : zero4());
             st4(&sm.consts[1][so], ok ? ld_cg4(job.I1wy + o) : zero4());
             st4(&sm.consts[2][so], ok ? ld_cg4(job.grad + o) : zero4());
@@ -301,18 +309,20 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            const int so = (RPT * wq + r) * TW + 4 * lane;
+            const int so = so0 + r * TW;
             const float4 ix = *reinterpret_cast<const float4 *>(&sm.consts[0][so]);
             const float4 iy = *reinterpret_cast<const float4 *>(&sm.consts[1][so]);
             const float4 g = *reinterpret_cast<const float4 *>(&sm.consts[2][so]);
             const float4 rc = *reinterpret_cast<const float4 *>(&sm.consts[3][so]);
+            const float4 o1 = *reinterpret_cast<const float4 *>(&sm.u[0][so]);
+            const float4 o2 = *reinterpret_cast<const float4 *>(&sm.u[1][so]);
             float l11 = __shfl_up_sync(0xffffffffu, p11[r].w, 1);
             float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
             if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
             float4 n1, n2;
 #define DFB_PRIMAL(C, PL11, PL21)                                                                      \
     {                                                                                                  \
-        const float rho = rc.C + (ix.C * u1[r].C + iy.C * u2[r].C);                                    \
+        const float rho = rc.C + (ix.C * o1.C + iy.C * o2.C);                                          \
         const float thr = l_t * g.C;                                                                   \
         float f = g.C > FLT_EPSILON ? f_div(-rho, g.C) : 0.f;                                          \
         f = rho > thr ? -l_t : f;                                                                      \
@@ -320,8 +330,8 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         const float d1 = f * ix.C, d2 = f * iy.C;                                                      \
         const float div1 = (p11[r].C - (PL11)) + (p12[r].C - up12.C);                                  \
         const float div2 = (p21[r].C - (PL21)) + (p22[r].C - up22.C);                                  \
-        n1.C = (u1[r].C + d1) + theta * div1;                                                          \
-        n2.C = (u2[r].C + d2) + theta * div2;                                                          \
+        n1.C = (o1.C + d1) + theta * div1;                                                             \
+        n2.C = (o2.C + d2) + theta * div2;                                                             \
     }
             DFB_PRIMAL(x, l11, l21)
             DFB_PRIMAL(y, p11[r].x, p21[r].x)
@@ -332,10 +342,10 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
                 const int ry = RPT * wq + r;
                 if (lane_in && ry >= ry_lo && ry < ry_hi && gy0 + r < H) {
                     // diff = (u1-u1')^2 + (u2-u2')^2 per pixel (fp32, as the reference's diff plane)
-                    err += (u1[r].x - n1.x) * (u1[r].x - n1.x) + (u2[r].x - n2.x) * (u2[r].x - n2.x);
-                    if (gx0 + 1 < W) err += (u1[r].y - n1.y) * (u1[r].y - n1.y) + (u2[r].y - n2.y) * (u2[r].y - n2.y);
-                    if (gx0 + 2 < W) err += (u1[r].z - n1.z) * (u1[r].z - n1.z) + (u2[r].z - n2.z) * (u2[r].z - n2.z);
-                    if (gx0 + 3 < W) err += (u1[r].w - n1.w) * (u1[r].w - n1.w) + (u2[r].w - n2.w) * (u2[r].w - n2.w);
+                    err += (o1.x - n1.x) * (o1.x - n1.x) + (o2.x - n2.x) * (o2.x - n2.x);
+                    if (gx0 + 1 < W) err += (o1.y - n1.y) * (o1.y - n1.y) + (o2.y - n2.y) * (o2.y - n2.y);
+                    if (gx0 + 2 < W) err += (o1.z - n1.z) * (o1.z - n1.z) + (o2.z - n2.z) * (o2.z - n2.z);
+                    if (gx0 + 3 < W) err += (o1.w - n1.w) * (o1.w - n1.w) + (o2.w - n2.w) * (o2.w - n2.w);
                 }
             }
             if (edge_x) {  // mirror the last image column into the pixel right of it: u(x+1) - u(x) == 0 there
@@ -343,46 +353,51 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
                 if (jlast == 1) { n1.z = n1.y; n2.z = n2.y; }
                 if (jlast == 2) { n1.w = n1.z; n2.w = n2.z; }
             }
-            u1[r] = n1;
-            u2[r] = n2;
+            st4(&sm.u[0][so], n1);
+            st4(&sm.u[1][so], n2);
+            if (edge_y && r > 0 && r - 1 == rbot) {  // first out-of-image row: mirror the last image row into it
+                const float4 m1 = *reinterpret_cast<const float4 *>(&sm.u[0][so - TW]);
+                const float4 m2 = *reinterpret_cast<const float4 *>(&sm.u[1][so - TW]);
+                st4(&sm.u[0][so], m1);
+                st4(&sm.u[1][so], m2);
+            }
             up12 = p12[r];
             up22 = p22[r];
         }
-        if (edge_y) {  // mirror the last image row into the row below it
-#pragma unroll
-            for (int r = 0; r < RPT - 1; ++r)
-                if (r == rbot) {
-                    u1[r + 1] = u1[r];
-                    u2[r + 1] = u2[r];
-                }
-        }
-        st4(&sm.u_top[0][wq][4 * lane], u1[0]);
-        st4(&sm.u_top[1][wq][4 * lane], u2[0]);
         signal(&prog[wq], base + 2 * it + 1);
         if (!flagsync) __syncthreads();
         // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ------------------------
-        float4 dn1 = u1[RPT - 1], dn2 = u2[RPT - 1];  // region's last row: halo, or mirrored image border
-        if (wq < kWarps - 1) {
-            if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1);
-            if (!(edge_y && rbot == RPT - 1)) {
-                dn1 = *reinterpret_cast<const float4 *>(&sm.u_top[0][wq + 1][4 * lane]);
-                dn2 = *reinterpret_cast<const float4 *>(&sm.u_top[1][wq + 1][4 * lane]);
-            }
-        }
+        float4 c1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0]);
+        float4 c2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0]);
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            const float4 d1 = r < RPT - 1 ? u1[r + 1] : dn1;
-            const float4 d2 = r < RPT - 1 ? u2[r + 1] : dn2;
-            float r1 = __shfl_down_sync(0xffffffffu, u1[r].x, 1);
-            float r2 = __shfl_down_sync(0xffffffffu, u2[r].x, 1);
-            if (edge_x && jlast == 3) {
-                r1 = u1[r].w;
-                r2 = u2[r].w;
+            float4 d1, d2;
+            if (r < RPT - 1) {
+                d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + (r + 1) * TW]);
+                d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + (r + 1) * TW]);
+            } else {
+                d1 = c1;  // region's last row: halo, or the mirrored image border
+                d2 = c2;
+                if (wq < kWarps - 1) {
+                    if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1);
+                    if (!(edge_y && rbot == RPT - 1)) {
+                        d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
+                        d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
+                    }
+                }
             }
-            tvl1_dual_px(u1[r].y - u1[r].x, d1.x - u1[r].x, u2[r].y - u2[r].x, d2.x - u2[r].x, taut, p11[r].x, p12[r].x, p21[r].x, p22[r].x);
-            tvl1_dual_px(u1[r].z - u1[r].y, d1.y - u1[r].y, u2[r].z - u2[r].y, d2.y - u2[r].y, taut, p11[r].y, p12[r].y, p21[r].y, p22[r].y);
-            tvl1_dual_px(u1[r].w - u1[r].z, d1.z - u1[r].z, u2[r].w - u2[r].z, d2.z - u2[r].z, taut, p11[r].z, p12[r].z, p21[r].z, p22[r].z);
-            tvl1_dual_px(r1 - u1[r].w, d1.w - u1[r].w, r2 - u2[r].w, d2.w - u2[r].w, taut, p11[r].w, p12[r].w, p21[r].w, p22[r].w);
+            float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, c2.x, 1);
+            if (edge_x && jlast == 3) {
+                r1 = c1.w;
+                r2 = c2.w;
+            }
+            tvl1_dual_px(c1.y - c1.x, d1.x - c1.x, c2.y - c2.x, d2.x - c2.x, taut, p11[r].x, p12[r].x, p21[r].x, p22[r].x);
+            tvl1_dual_px(c1.z - c1.y, d1.y - c1.y, c2.z - c2.y, d2.y - c2.y, taut, p11[r].y, p12[r].y, p21[r].y, p22[r].y);
+            tvl1_dual_px(c1.w - c1.z, d1.z - c1.z, c2.w - c2.z, d2.z - c2.z, taut, p11[r].z, p12[r].z, p21[r].z, p22[r].z);
+            tvl1_dual_px(r1 - c1.w, d1.w - c1.w, r2 - c2.w, d2.w - c2.w, taut, p11[r].w, p12[r].w, p21[r].w, p22[r].w);
+            c1 = d1;
+            c2 = d2;
         }
         st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
         st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
@@ -403,8 +418,8 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             const int ry = RPT * wq + r, gy = gy0 + r;
             if (lane_in && ry >= ry_lo && ry < ry_hi && gy < H) {
                 const size_t o = (size_t)gy * P + gx0;
-                st4(d0 + o, u1[r]);
-                st4(d1 + o, u2[r]);
+                st4(d0 + o, *reinterpret_cast<const float4 *>(&sm.u[0][so0 + r * TW]));
+                st4(d1 + o, *reinterpret_cast<const float4 *>(&sm.u[1][so0 + r * TW]));
                 st4(d2 + o, p11[r]);
                 st4(d3 + o, p12[r]);
                 st4(d4 + o, p21[r]);

@@ -55,7 +55,10 @@ __host__ __device__ inline int fused_tiles_along(int n, int T, int h) {
     const int stride = T - 2 * h;
     return n <= T ? 1 : (n - 2 * h + stride - 1) / stride;
 }
-constexpr int kFusedTileW = 128, kFusedTileH = 64;
+#ifndef DFB_FUSED_THREADS
+#define DFB_FUSED_THREADS 512
+#endif
+constexpr int kFusedTileW = 128, kFusedTileH = DFB_FUSED_THREADS / 32 * 4;
 
 int fused_num_sms(int device);
 // returns the number of kernels launched
