@@ -131,38 +131,12 @@ __device__ __forceinline__ void phase_warp(const int G, const int bid, const Fus
     for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int y = i / W, x = i - y * W;
         const size_t o = (size_t)y * P + x;
-        const float u1v = u1[o], u2v = u2[o];
-        const float wx = x + u1v, wy = y + u2v;
-        const int xmin = (int)ceilf(wx - 2.0f), ymin = (int)ceilf(wy - 2.0f);
-        float kx[4], ky[4];
-        int cxs[4];
-        size_t rows[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            kx[t] = bicubic_coeff(wx - (float)(xmin + t));
-            ky[t] = bicubic_coeff(wy - (float)(ymin + t));
-            cxs[t] = max(0, min(xmin + t, W - 1));
-            rows[t] = (size_t)max(0, min(ymin + t, H - 1)) * P;
-        }
-        float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const float wgt = kx[b] * ky[a];
-                const size_t t = rows[a] + cxs[b];
-                sum = sum + wgt * __ldg(I1 + t);
-                sumx = sumx + wgt * I1x[t];
-                sumy = sumy + wgt * I1y[t];
-                wsum = wsum + wgt;
-            }
-        }
-        const float coeff = f_rcp(wsum);
-        const float I1wv = sum * coeff, ix = sumx * coeff, iy = sumy * coeff;
+        float ix, iy, g, rc;
+        tvl1_warp_px(I1, I1x, I1y, W, H, P, x, y, u1[o], u2[o], __ldg(L.I0 + o), ix, iy, g, rc);
         job.I1wx[o] = ix;
         job.I1wy[o] = iy;
-        job.grad[o] = ix * ix + iy * iy;
-        job.rho_c[o] = I1wv - ix * u1v - iy * u2v - __ldg(L.I0 + o);
+        job.grad[o] = g;
+        job.rho_c[o] = rc;
     }
 }
 
@@ -245,7 +219,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
     const int rx0 = tx * (TW - 2 * hx), ry0 = ty * (TH - 2 * hy);
     const int gx0 = rx0 + 4 * lane;
     const int gy0 = ry0 + RPT * wq;
-    const float l_t = job.c.l_t, taut = job.c.taut, theta = job.c.theta;
+    const float taut = job.c.taut;
     volatile int *prog = sm.prog;
     const bool flagsync = job.flag_sync != 0;  // 0: CTA-wide barriers between half-steps (debug / comparison)
 
@@ -320,24 +294,10 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
             if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
             float4 n1, n2;
-#define DFB_PRIMAL(C, PL11, PL21)                                                                      \
-    {                                                                                                  \
-        const float rho = rc.C + (ix.C * o1.C + iy.C * o2.C);                                          \
-        const float thr = l_t * g.C;                                                                   \
-        float f = g.C > FLT_EPSILON ? f_div(-rho, g.C) : 0.f;                                          \
-        f = rho > thr ? -l_t : f;                                                                      \
-        f = rho < -thr ? l_t : f;                                                                      \
-        const float d1 = f * ix.C, d2 = f * iy.C;                                                      \
-        const float div1 = (p11[r].C - (PL11)) + (p12[r].C - up12.C);                                  \
-        const float div2 = (p21[r].C - (PL21)) + (p22[r].C - up22.C);                                  \
-        n1.C = (o1.C + d1) + theta * div1;                                                             \
-        n2.C = (o2.C + d2) + theta * div2;                                                             \
-    }
-            DFB_PRIMAL(x, l11, l21)
-            DFB_PRIMAL(y, p11[r].x, p21[r].x)
-            DFB_PRIMAL(z, p11[r].y, p21[r].y)
-            DFB_PRIMAL(w, p11[r].z, p21[r].z)
-#undef DFB_PRIMAL
+            tvl1_primal_px(ix.x, iy.x, g.x, rc.x, o1.x, o2.x, (p11[r].x - l11) + (p12[r].x - up12.x), (p21[r].x - l21) + (p22[r].x - up22.x), job.c, n1.x, n2.x);
+            tvl1_primal_px(ix.y, iy.y, g.y, rc.y, o1.y, o2.y, (p11[r].y - p11[r].x) + (p12[r].y - up12.y), (p21[r].y - p21[r].x) + (p22[r].y - up22.y), job.c, n1.y, n2.y);
+            tvl1_primal_px(ix.z, iy.z, g.z, rc.z, o1.z, o2.z, (p11[r].z - p11[r].y) + (p12[r].z - up12.z), (p21[r].z - p21[r].y) + (p22[r].z - up22.z), job.c, n1.z, n2.z);
+            tvl1_primal_px(ix.w, iy.w, g.w, rc.w, o1.w, o2.w, (p11[r].w - p11[r].z) + (p12[r].w - up12.w), (p21[r].w - p21[r].z) + (p22[r].w - up22.w), job.c, n1.w, n2.w);
             if (do_err) {
                 const int ry = RPT * wq + r;
                 if (lane_in && ry >= ry_lo && ry < ry_hi && gy0 + r < H) {

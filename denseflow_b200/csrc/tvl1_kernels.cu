@@ -73,31 +73,13 @@ __global__ void k_warp_backward(Plane I0, Plane I1, Plane I1x, Plane I1y, Plane 
     const int x = blockIdx.x * BX + threadIdx.x;
     const int y = blockIdx.y * BY + threadIdx.y;
     if (x >= I0.w || y >= I0.h) return;
-    const int W = I0.w, H = I0.h;
     const size_t i = (size_t)y * I0.pitch + x;  // all level planes share one pitch
-    const float u1v = u1.p[i], u2v = u2.p[i];
-    const float wx = x + u1v, wy = y + u2v;
-    const int xmin = (int)ceilf(wx - 2.0f), xmax = (int)floorf(wx + 2.0f);
-    const int ymin = (int)ceilf(wy - 2.0f), ymax = (int)floorf(wy + 2.0f);
-    float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
-    for (int cy = ymin; cy <= ymax; ++cy) {
-        const float wyc = bicubic_coeff(wy - cy);
-        const size_t ro = (size_t)max(0, min(cy, H - 1)) * I1.pitch;
-        for (int cx = xmin; cx <= xmax; ++cx) {
-            const float wgt = bicubic_coeff(wx - cx) * wyc;
-            const size_t o = ro + max(0, min(cx, W - 1));
-            sum = sum + wgt * __ldg(I1.p + o);
-            sumx = sumx + wgt * __ldg(I1x.p + o);
-            sumy = sumy + wgt * __ldg(I1y.p + o);
-            wsum = wsum + wgt;
-        }
-    }
-    const float coeff = f_rcp(wsum);
-    const float I1wv = sum * coeff, ix = sumx * coeff, iy = sumy * coeff;
+    float ix, iy, g, rc;
+    tvl1_warp_px(I1.p, I1x.p, I1y.p, I0.w, I0.h, I0.pitch, x, y, u1.p[i], u2.p[i], I0.p[i], ix, iy, g, rc);
     I1wx.p[i] = ix;
     I1wy.p[i] = iy;
-    grad.p[i] = ix * ix + iy * iy;
-    rho_c.p[i] = I1wv - ix * u1v - iy * u2v - I0.p[i];
+    grad.p[i] = g;
+    rho_c.p[i] = rc;
 }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }

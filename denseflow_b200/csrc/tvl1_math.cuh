@@ -15,20 +15,14 @@ namespace dfb {
 __device__ __forceinline__ void tvl1_primal_px(float ix, float iy, float g, float rc, float u1o, float u2o,
                                                float div1, float div2, const Tvl1Consts &c, float &u1n,
                                                float &u2n) {
+    // The reference's three-way branch (rho < -l_t*g | rho > l_t*g | g > eps) as a branch-free factor f with
+    // d = f * (I1wx, I1wy): f = +l_t, -l_t, -rho/g or 0.  Same products, no divergent code.
     const float rho = rc + (ix * u1o + iy * u2o);
     const float thr = c.l_t * g;
-    float d1 = 0.f, d2 = 0.f;
-    if (rho < -thr) {
-        d1 = c.l_t * ix;
-        d2 = c.l_t * iy;
-    } else if (rho > thr) {
-        d1 = -c.l_t * ix;
-        d2 = -c.l_t * iy;
-    } else if (g > FLT_EPSILON) {
-        const float fi = f_div(-rho, g);
-        d1 = fi * ix;
-        d2 = fi * iy;
-    }
+    float f = g > FLT_EPSILON ? f_div(-rho, g) : 0.f;
+    f = rho > thr ? -c.l_t : f;
+    f = rho < -thr ? c.l_t : f;
+    const float d1 = f * ix, d2 = f * iy;
     u1n = (u1o + d1) + c.theta * div1;
     u2n = (u2o + d2) + c.theta * div2;
 }
@@ -61,6 +55,46 @@ __device__ __forceinline__ float bicubic_coeff(float x) {
     if (x <= 1.0f) return x * x * (1.5f * x - 2.5f) + 1.0f;
     if (x < 2.0f) return x * (x * (-0.5f * x + 2.5f) - 4.0f) + 2.0f;
     return 0.0f;
+}
+
+// A.2 "Warp (warpBackward)" for one pixel.  The reference sums taps cx = ceil(wx-2) .. floor(wx+2) (4, or 5 when wx
+// is integral, in which case both end taps have weight k(+-2) = 0).  Anchored at xmin = ceil(wx-2) the distance to tap
+// xmin+4 is in [2,3), so its weight is always exactly 0: a fixed 4x4 window with separable weights gives the same sums
+// (tap order preserved: rows outer, columns inner).  I1 / I1x / I1y share one pitch; clamp addressing.
+__device__ __forceinline__ void tvl1_warp_px(const float *__restrict__ I1, const float *I1x, const float *I1y, int W, int H, int P,
+                                             int x, int y, float u1v, float u2v, float I0v, float &ix, float &iy, float &grad,
+                                             float &rho_c) {
+    const float wx = x + u1v, wy = y + u2v;
+    const int xmin = (int)ceilf(wx - 2.0f), ymin = (int)ceilf(wy - 2.0f);
+    float kx[4], ky[4];
+    int cxs[4];
+    size_t rows[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        kx[t] = bicubic_coeff(wx - (float)(xmin + t));
+        ky[t] = bicubic_coeff(wy - (float)(ymin + t));
+        cxs[t] = max(0, min(xmin + t, W - 1));
+        rows[t] = (size_t)max(0, min(ymin + t, H - 1)) * P;
+    }
+    float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float wgt = kx[b] * ky[a];
+            const size_t t = rows[a] + cxs[b];
+            sum = sum + wgt * __ldg(I1 + t);
+            sumx = sumx + wgt * I1x[t];
+            sumy = sumy + wgt * I1y[t];
+            wsum = wsum + wgt;
+        }
+    }
+    const float coeff = f_rcp(wsum);
+    const float I1wv = sum * coeff;
+    ix = sumx * coeff;
+    iy = sumy * coeff;
+    grad = ix * ix + iy * iy;
+    rho_c = I1wv - ix * u1v - iy * u2v - I0v;
 }
 
 }  // namespace dfb
