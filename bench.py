@@ -216,6 +216,8 @@ def main():
     import denseflow_b200 as d
     from denseflow_b200 import shard
 
+    # keep stdout to the one JSON line: NCCL's own log lines (e.g. "NCCL version ...") go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local_rank, world = shard.init()
     if world != args.gpus and rank == 0:
         print("warning: WORLD_SIZE=%d but --gpus=%d" % (world, args.gpus), file=sys.stderr)
