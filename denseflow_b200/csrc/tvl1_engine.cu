@@ -33,6 +33,7 @@ struct Tvl1Params {
     int fused_k = 8;
     int flag_sync = 1;
     int time_kernels = 0;
+    int use_tma = 1;
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
@@ -48,6 +49,7 @@ class Tvl1 final : public FlowAlgorithm {
         for (auto &l : lanes_) {
             if (l.host_ctl) cudaFreeHost(l.host_ctl);
             if (l.own) cudaFree(l.own);
+            if (l.tmaps) cudaFree(l.tmaps);
         }
         if (stats_event_) cudaEventDestroy(stats_event_);
     }
@@ -76,6 +78,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
         else if (k == "flag_sync") prm_.flag_sync = v != 0;
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
+        else if (k == "use_tma") prm_.use_tma = v != 0;
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -93,6 +96,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "fused_k") *v = prm_.fused_k;
         else if (k == "flag_sync") *v = prm_.flag_sync;
         else if (k == "time_kernels") *v = prm_.time_kernels;
+        else if (k == "use_tma") *v = prm_.use_tma;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -250,6 +254,8 @@ class Tvl1 final : public FlowAlgorithm {
         double *partials = nullptr;
         unsigned *sync = nullptr;
         FusedHostCtl *host_ctl = nullptr, *dev_ctl = nullptr;
+        void *tmaps = nullptr;  // device array CUtensorMap[kMaxScales][kFusedMapsPerLevel]
+        int tmap_w = 0, tmap_h = 0, tmap_n = 0;
     };
 
     void ensure_lanes(int n) {
@@ -278,6 +284,7 @@ class Tvl1 final : public FlowAlgorithm {
             DFB_CUDA(cudaHostAlloc(&l.host_ctl, sizeof(FusedHostCtl), cudaHostAllocMapped));
             std::memset(l.host_ctl, 0, sizeof(FusedHostCtl));
             DFB_CUDA(cudaHostGetDevicePointer(&l.dev_ctl, l.host_ctl, 0));
+            DFB_CUDA(cudaMalloc(&l.tmaps, (size_t)kMaxScales * kFusedMapsPerLevel * kTensorMapBytes));
             lanes_.push_back(l);
         }
     }
@@ -351,6 +358,25 @@ class Tvl1 final : public FlowAlgorithm {
         accumulate_pixel_iters();
     }
 
+    // TMA descriptors of the lane's shared-memory-resident planes, rebuilt only when the frame geometry changes
+    void ensure_tensor_maps(Lane &wk, const LevelGeom *lv, int n) {
+        if (wk.tmap_w == lv[0].w && wk.tmap_h == lv[0].h && wk.tmap_n == n) return;
+        std::vector<char> host((size_t)kMaxScales * kFusedMapsPerLevel * kTensorMapBytes, 0);
+        for (int l = 0; l < n; ++l) {
+            char *m = host.data() + (size_t)l * kFusedMapsPerLevel * kTensorMapBytes;
+            float *planes[kFusedMapsPerLevel] = {wk.I1wx, wk.I1wy, wk.grad, wk.rho_c, level_plane(wk.u1pyr[0], lv, l).p,
+                                                 level_plane(wk.u2pyr[0], lv, l).p, level_plane(wk.u1pyr[1], lv, l).p,
+                                                 level_plane(wk.u2pyr[1], lv, l).p};
+            for (int k = 0; k < kFusedMapsPerLevel; ++k)
+                fused_encode_tensor_map(m + (size_t)k * kTensorMapBytes, planes[k], lv[l].w, lv[l].h, lv[l].pitch);
+        }
+        DFB_CUDA(cudaDeviceSynchronize());  // the previous maps may still be in use by a running launch
+        DFB_CUDA(cudaMemcpy(wk.tmaps, host.data(), host.size(), cudaMemcpyHostToDevice));
+        wk.tmap_w = lv[0].w;
+        wk.tmap_h = lv[0].h;
+        wk.tmap_n = n;
+    }
+
     // ---- fused = 1 -------------------------------------------------------------------------------
     void solve_fused(const PairJob *jobs, int count, const LevelGeom *lv, int n, cudaStream_t s) {
         ensure_lanes(count);
@@ -366,6 +392,9 @@ class Tvl1 final : public FlowAlgorithm {
             job.epsilon = prm_.epsilon;
             job.k = prm_.fused_k;
             job.flag_sync = prm_.flag_sync;
+            job.use_tma = prm_.use_tma;
+            if (prm_.use_tma) ensure_tensor_maps(wk, lv, n);
+            job.tmaps = wk.tmaps;
             job.c = Tvl1Consts{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};
             job.up_mul = (float)(1.0 / prm_.scale_step);
             for (int l = 0; l < n; ++l) {

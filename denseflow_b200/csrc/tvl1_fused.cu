@@ -24,6 +24,8 @@
 // branch of the A.4 state machine and results are run-to-run deterministic.
 #include <cfloat>
 
+#include <cuda.h>
+
 #include "tvl1_fused.cuh"
 #include "tvl1_math.cuh"
 
@@ -51,6 +53,7 @@ struct Smem {
     int ibcast[4];
     unsigned long long prof[32];
     int prog[kWarps];  // per-warp progress counters of the tile loop (see process_tile)
+    unsigned long long tma_bar;  // mbarrier the TMA tile loads complete on
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
@@ -62,6 +65,37 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers ---------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 2-D tile load global -> shared, completion signalled on the mbarrier (zero fill outside the tensor)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- grid barrier ---------------------------------------------------------------------------
 // sync[0] counts arrivals monotonically: barrier number b of a lane completes when it reaches b * G
@@ -210,8 +244,9 @@ __device__ __forceinline__ void signal(volatile int *flag, int v) {
     }
 }
 
-__device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLevel &L, int cur, int tx, int ty, int kk,
-                                           int hx, int hy, bool check, int base, Smem &sm, bool prof_on) {
+__device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLevel &L, int level, int cur, int tx, int ty,
+                                              int kk, int hx, int hy, bool check, int base, unsigned tma_parity, Smem &sm,
+                                              bool prof_on) {
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     unsigned long long t0 = 0;
     if (prof_on) t0 = gtime();
@@ -225,9 +260,28 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
 
     float4 p11[RPT], p12[RPT], p21[RPT], p22[RPT];
     const int so0 = (RPT * wq) * TW + 4 * lane;  // this thread's slot in row 0 of its warp (thread-private in smem planes)
-    // The warp above reads this warp's first u row in its dual steps: it must have finished the previous
-    // tile (its counter reached base - 2 = "last dual step of the previous tile done") before the row is overwritten.
-    if (flagsync && wq > 0) wait_ge(&prog[wq - 1], base - 2);
+    const bool use_tma = job.use_tma != 0;
+    if (use_tma) {
+        // One thread stages the six shared-memory-resident planes of the tile (4 constants + u1,u2: 192 KB) with
+        // TMA while every thread loads its share of the four dual planes into registers.  All warps must be done
+        // with the previous tile's shared memory first (the bulk copy overwrites every slot).
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const char *maps = static_cast<const char *>(job.tmaps) + (size_t)level * kFusedMapsPerLevel * kTensorMapBytes;
+            mbar_expect_tx(&sm.tma_bar, 6u * kConstPlane * (unsigned)sizeof(float));
+            tma_load_2d(sm.consts[0], maps + 0 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+            tma_load_2d(sm.consts[1], maps + 1 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+            tma_load_2d(sm.consts[2], maps + 2 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+            tma_load_2d(sm.consts[3], maps + 3 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+            tma_load_2d(sm.u[0], maps + (4 + 2 * cur) * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+            tma_load_2d(sm.u[1], maps + (5 + 2 * cur) * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
+        }
+    } else if (flagsync && wq > 0) {
+        // The warp above reads this warp's first u row in its dual steps: it must have finished the previous tile
+        // (its counter reached base - 2 = "last dual step of the previous tile done") before the row is overwritten.
+        wait_ge(&prog[wq - 1], base - 2);
+    }
     {
         const float *s0 = L.u1[cur], *s1 = L.u2[cur], *s2 = job.p[cur][0], *s3 = job.p[cur][1], *s4 = job.p[cur][2],
                     *s5 = job.p[cur][3];
@@ -241,15 +295,18 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             p12[r] = ok ? ld_cg4(s3 + o) : zero4();
             p21[r] = ok ? ld_cg4(s4 + o) : zero4();
             p22[r] = ok ? ld_cg4(s5 + o) : zero4();
-            const int so = so0 + r * TW;
-            st4(&sm.u[0][so], ok ? ld_cg4(s0 + o) : zero4());
-            st4(&sm.u[1][so], ok ? ld_cg4(s1 + o) : zero4());
-            st4(&sm.consts[0][so], ok ? ld_cg4(job.I1wx + o) : zero4());
-            st4(&sm.consts[1][so], ok ? ld_cg4(job.I1wy + o) : zero4());
-            st4(&sm.consts[2][so], ok ? ld_cg4(job.grad + o) : zero4());
-            st4(&sm.consts[3][so], ok ? ld_cg4(job.rho_c + o) : zero4());
+            if (!use_tma) {
+                const int so = so0 + r * TW;
+                st4(&sm.u[0][so], ok ? ld_cg4(s0 + o) : zero4());
+                st4(&sm.u[1][so], ok ? ld_cg4(s1 + o) : zero4());
+                st4(&sm.consts[0][so], ok ? ld_cg4(job.I1wx + o) : zero4());
+                st4(&sm.consts[1][so], ok ? ld_cg4(job.I1wy + o) : zero4());
+                st4(&sm.consts[2][so], ok ? ld_cg4(job.grad + o) : zero4());
+                st4(&sm.consts[3][so], ok ? ld_cg4(job.rho_c + o) : zero4());
+            }
         }
     }
+    if (use_tma) mbar_wait(&sm.tma_bar, tma_parity);
     // image borders inside this tile's region (tile-uniform)
     const bool edge_x = W - 1 >= rx0 && W - 1 < rx0 + TW;
     const bool edge_y = H - 1 >= ry0 && H - 1 < ry0 + TH;
@@ -433,7 +490,7 @@ struct Prof {
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant__ FusedBatch batch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int G = batch.group;
     const int lane_id = blockIdx.x / G, bid = blockIdx.x - lane_id * G;
@@ -443,9 +500,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
     int cur = 0;
     unsigned long long px_iters = 0;
     int tile_base = 1;  // progress-counter epoch of the tile loop (sm.prog starts at 0)
+    unsigned tma_parity = 0;
     Prof prof;
     prof.init(sm.prof, bid == 0);
     if (threadIdx.x < kWarps) sm.prog[threadIdx.x] = 0;
+    if (threadIdx.x == 0) mbar_init(&sm.tma_bar, 1);
     __syncthreads();
 
     for (int s = job.nscales - 1; s >= 0; --s) {
@@ -490,8 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     const int ntiles = ntx * nty;
                     for (int t = bid; t < ntiles; t += G) {
                         const int ty = t / ntx, tx = t - ty * ntx;
-                        const float e = process_tile(job, L, cur, tx, ty, kk, hx, hy, chk, tile_base, sm, prof.on);
+                        const float e = process_tile(job, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on);
                         tile_base += 2 * kk + 2;
+                        tma_parity ^= 1u;
                         if (chk) {
                             const double bs = block_sum((double)e, sm);
                             if (threadIdx.x == 0) cta_err += bs;
@@ -554,6 +614,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
 }
 
 }  // namespace
+
+void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pitch) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    static_assert(sizeof(CUtensorMap) == kTensorMapBytes, "CUtensorMap size");
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TW, (cuuint32_t)TH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+}
 
 int fused_num_sms(int device) {
     static int num_sms[64] = {};

@@ -28,6 +28,9 @@ struct FusedHostCtl {
 struct FusedJob {
     int nscales, warps, iterations, k;
     int flag_sync;  // 1: neighbour-warp progress counters in the tile loop, 0: CTA-wide barriers
+    int use_tma;    // 1: constants + u tiles staged by TMA (cp.async.bulk.tensor.2d), 0: LDG -> STS
+    // CUtensorMap[nscales][kFusedMapsPerLevel] in global memory: I1wx, I1wy, grad, rho_c, u1[0], u2[0], u1[1], u2[1]
+    const void *tmaps;
     double epsilon;
     Tvl1Consts c;
     float up_mul;
@@ -45,6 +48,8 @@ struct FusedJob {
 // their own barrier words, partials and workspace.  Coarse pyramid levels have fewer tiles than the
 // GPU has SMs; running pairs side by side keeps every SM busy without touching a pair's arithmetic.
 constexpr int kFusedMaxLanes = 8;
+constexpr int kFusedMapsPerLevel = 8;
+constexpr int kTensorMapBytes = 128;  // sizeof(CUtensorMap)
 struct FusedBatch {
     int njobs, group;
     FusedJob job[kFusedMaxLanes];
@@ -61,6 +66,9 @@ __host__ __device__ inline int fused_tiles_along(int n, int T, int h) {
 constexpr int kFusedTileW = 128, kFusedTileH = DFB_FUSED_THREADS / 32 * 4;
 
 int fused_num_sms(int device);
+// Encodes one 2-D fp32 tile descriptor (box 128 x 64, no swizzle, zero fill out of bounds) into out[128 bytes].
+// plane: base pointer, extent w x h (elements / rows), row pitch in elements.
+void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pitch);
 // returns the number of kernels launched
 int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s);
 

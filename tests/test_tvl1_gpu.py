@@ -144,11 +144,12 @@ def test_fused_schedule_is_deterministic_and_lane_invariant():
     out bit-identical for every lane count, for flag vs CTA-barrier synchronisation, for every k, and run to run."""
     fr = synth.stream(360, 640, 9, seed=31)
     ref = None
-    for lanes, flag_sync, k in [(1, 0, 8), (1, 1, 8), (2, 1, 8), (4, 1, 8), (8, 1, 8), (8, 1, 8), (3, 1, 5), (0, 1, 3), (0, 0, 1)]:
-        e = _engine("default", 640, 360, lanes=lanes, flag_sync=flag_sync, fused_k=k)
+    for lanes, flag_sync, k, tma in [(1, 0, 8, 0), (1, 1, 8, 1), (2, 1, 8, 1), (4, 1, 8, 0), (8, 1, 8, 1), (8, 1, 8, 1), (3, 1, 5, 1),
+                                     (0, 1, 3, 1), (0, 0, 1, 1), (0, 0, 2, 0)]:
+        e = _engine("default", 640, 360, lanes=lanes, flag_sync=flag_sync, fused_k=k, use_tma=tma)
         out = e.calc_batch(list(fr), step=1)
         if ref is None:
             ref = out
-        assert np.array_equal(out, ref), (lanes, flag_sync, k)
+        assert np.array_equal(out, ref), (lanes, flag_sync, k, tma)
     unfused = _engine("default", 640, 360, fused=0).calc_batch(list(fr[:3]), step=1)
     assert np.array_equal(unfused, ref[:2])
