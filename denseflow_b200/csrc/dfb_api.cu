@@ -24,7 +24,7 @@ struct dfb_handle {
     // host-path plumbing: three streams so H2D of frame i+1, compute of pair i and D2H of flow i-1 overlap
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
     static constexpr int kFrameRing = 16; // device u8 frames (dead as soon as their pyramid is built)
-    static constexpr int kFlowRing = 16;  // device flow / quantised outputs (two launches of up to 8 pairs in flight)
+    static constexpr int kFlowRing = 32;  // device flow / quantised outputs (two launches of up to 16 pairs in flight)
     uint8_t *d_frame[kFrameRing] = {};
     size_t d_frame_pitch = 0;
     float *d_flow[kFlowRing] = {};
@@ -80,6 +80,20 @@ int check_size(dfb_handle *h, int w, int h_) {
     return DFB_OK;
 }
 
+// pinned staging buffers exist only for callers that pass pageable memory: allocated on first use
+uint8_t *stage_frame(dfb_handle *h, int r) {
+    if (!h->h_frame[r]) DFB_CUDA(cudaHostAlloc(&h->h_frame[r], (size_t)h->max_w * h->max_h, cudaHostAllocDefault));
+    return h->h_frame[r];
+}
+float *stage_flow(dfb_handle *h, int r) {
+    if (!h->h_flow[r]) DFB_CUDA(cudaHostAlloc(&h->h_flow[r], (size_t)h->max_w * h->max_h * 2 * sizeof(float), cudaHostAllocDefault));
+    return h->h_flow[r];
+}
+uint8_t *stage_q(dfb_handle *h, int r) {
+    if (!h->h_q[r]) DFB_CUDA(cudaHostAlloc(&h->h_q[r], (size_t)h->max_w * h->max_h * 2, cudaHostAllocDefault));
+    return h->h_q[r];
+}
+
 void ensure_host_path(dfb_handle *h) {
     if (h->s_in) return;
     DFB_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
@@ -89,7 +103,6 @@ void ensure_host_path(dfb_handle *h) {
     h->d_frame_pitch = fpitch;
     for (int i = 0; i < dfb_handle::kFrameRing; ++i) {
         DFB_CUDA(cudaMalloc(&h->d_frame[i], fpitch * h->max_h));
-        DFB_CUDA(cudaHostAlloc(&h->h_frame[i], (size_t)h->max_w * h->max_h, cudaHostAllocDefault));
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming));
     }
@@ -97,8 +110,6 @@ void ensure_host_path(dfb_handle *h) {
         DFB_CUDA(cudaMalloc(&h->d_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float)));
         DFB_CUDA(cudaMalloc(&h->d_qx[i], (size_t)h->max_w * h->max_h));
         DFB_CUDA(cudaMalloc(&h->d_qy[i], (size_t)h->max_w * h->max_h));
-        DFB_CUDA(cudaHostAlloc(&h->h_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float), cudaHostAllocDefault));
-        DFB_CUDA(cudaHostAlloc(&h->h_q[i], (size_t)h->max_w * h->max_h * 2, cudaHostAllocDefault));
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
@@ -131,7 +142,7 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             if (!is_pinned_or_device(src)) {
                 // the pinned staging buffer of this ring slot is free once its previous H2D finished
                 if (f >= FR) DFB_CUDA(cudaEventSynchronize(h->ev_in[r]));
-                std::memcpy(h->h_frame[r], src, fbytes);
+                std::memcpy(stage_frame(h, r), src, fbytes);
                 src = h->h_frame[r];
             }
             DFB_CUDA(cudaMemcpy2DAsync(h->d_frame[r], h->d_frame_pitch, src, w, w, hh, cudaMemcpyHostToDevice, h->s_in));
@@ -191,14 +202,14 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             const int j = j0 + i, ring = j % OR;
             if (bound > 0) {
                 const bool direct = is_pinned_or_device(qx[j]) && is_pinned_or_device(qy[j]);
-                uint8_t *dx = direct ? qx[j] : h->h_q[ring], *dy = direct ? qy[j] : h->h_q[ring] + fbytes;
+                uint8_t *dx = direct ? qx[j] : stage_q(h, ring), *dy = direct ? qy[j] : stage_q(h, ring) + fbytes;
                 DFB_CUDA(cudaMemcpyAsync(dx, h->d_qx[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
                 DFB_CUDA(cudaMemcpyAsync(dy, h->d_qy[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
                 if (!direct) pending_copy[ring] = j;
                 h->counters.d2h_bytes += 2 * fbytes;
             } else {
                 const bool direct = is_pinned_or_device(flows[j]);
-                DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : h->h_flow[ring], h->d_flow[ring], fbytes * 2 * sizeof(float),
+                DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : stage_flow(h, ring), h->d_flow[ring], fbytes * 2 * sizeof(float),
                                          cudaMemcpyDeviceToHost, h->s_out));
                 if (!direct) pending_copy[ring] = j;
                 h->counters.d2h_bytes += fbytes * 2 * sizeof(float);

@@ -21,7 +21,7 @@ namespace dfb {
 namespace {
 
 constexpr int kMaxLevels = 8;
-constexpr int kMaxHalf = 32;  // largest Gaussian half-width (smoothSize 39 at level 5 -> half 19)
+constexpr int kMaxHalf = 40;  // largest Gaussian half-width: level k = 5 has sigma 15.5 -> smoothSize 79 -> half 39
 
 struct FarnConsts {
     float g[8], xg[8], xxg[8];  // polyN <= 7
@@ -187,60 +187,75 @@ __global__ void __launch_bounds__(256) k_update_matrices(Plane fxp, Plane fyp, P
 }
 
 // ---- B.5 fused iteration: 13x13 box mean of the 5 planes of M -> 2x2 solve -> (optionally) rebuild M ------
-// One CTA produces a 32 x 16 tile of flow: the (32+12) x (16+12) window of each M plane is summed
-// vertically into shared memory (index-clamped), then horizontally; the solve and the rebuild of M for
-// the next iteration happen in registers.  M is double-buffered across iterations (Mout != Min): the
-// window of a neighbouring tile must still see this iteration's M.
-constexpr int BW = 32, BH = 16;
+// One CTA produces a 32 x 32 tile of flow.  The (32+12) x (32+12) window of each of the five M planes is staged
+// in shared memory once (index-clamped), summed vertically (centre + symmetric pairs, the reference's order) into a
+// second shared buffer, then horizontally; the solve and the rebuild of M for the next iteration happen in
+// registers.  Global reads of M drop from 13 vertical taps x 5 planes per column to 1.9 per output pixel and plane.
+// M is double-buffered across iterations (Mout != Min): a neighbouring tile's window must still see this iteration's M.
+constexpr int BW = 32, BH = 32;
 
 template <int HALF>
-__global__ void __launch_bounds__(BW *BH) k_box_solve_update(Plane5 Min, Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 Mout,
-                                                             int rebuild) {
-    constexpr int sw = BW + 2 * HALF;
-    __shared__ float vs[5][BH][sw];
+__global__ void __launch_bounds__(256) k_box_solve_update(Plane5 Min, Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 Mout,
+                                                           int rebuild) {
+    constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
+    extern __shared__ float box_smem[];
+    float(*raw)[sh][sw] = reinterpret_cast<float(*)[sh][sw]>(box_smem);               // [5][sh][sw]
+    float(*vs)[BH][sw] = reinterpret_cast<float(*)[BH][sw]>(box_smem + 5 * sh * sw);  // [5][BH][sw]
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
     const int w = Min.w, h = Min.h, pitch = Min.pitch;
-    const int tid = threadIdx.y * BW + threadIdx.x;
-    for (int i = tid; i < BH * sw; i += BW * BH) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < sh * sw; i += 256) {
         const int ty = i / sw, tx = i - ty * sw;
-        const int y = min(y0 + ty, h - 1);
+        const int y = max(0, min(y0 + ty - HALF, h - 1));
         const int x = max(0, min(x0 + tx - HALF, w - 1));
+        const size_t o = (size_t)y * pitch + x;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) raw[k][ty][tx] = Min.p[k][o];
+    }
+    __syncthreads();
+    // vertical sums.  Clamped rows are materialised in the window, except that the reference clamps the row index
+    // of the TAP (max(y-j,0), min(y+j,h-1)) — identical, because the window rows are themselves clamped copies.
+    for (int i = tid; i < BH * sw; i += 256) {
+        const int ty = i / sw, tx = i - ty * sw;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const float *s = Min.p[k];
-            float acc = s[(size_t)y * pitch + x];
+            float acc = raw[k][ty + HALF][tx];
 #pragma unroll
-            for (int j = 1; j <= HALF; ++j) acc = acc + (s[(size_t)max(y - j, 0) * pitch + x] + s[(size_t)min(y + j, h - 1) * pitch + x]);
+            for (int j = 1; j <= HALF; ++j) acc = acc + (raw[k][ty + HALF - j][tx] + raw[k][ty + HALF + j][tx]);
             vs[k][ty][tx] = acc;
         }
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= w || y >= h) return;
     constexpr float area_inv = 1.f / (float)((1 + 2 * HALF) * (1 + 2 * HALF));
-    float b[5];
+    for (int i = tid; i < BH * BW; i += 256) {
+        const int ty = i / BW, tx = i - ty * BW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= w || y >= h) continue;
+        float b[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const float *row = &vs[k][threadIdx.y][threadIdx.x + HALF];
-        float acc = row[0];
+        for (int k = 0; k < 5; ++k) {
+            const float *row = &vs[k][ty][tx + HALF];
+            float acc = row[0];
 #pragma unroll
-        for (int j = 1; j <= HALF; ++j) acc = acc + (row[-j] + row[j]);
-        b[k] = acc * area_inv;
-    }
-    // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
-    const float det_inv = f_rcp(b[0] * b[2] - b[1] * b[1] + 1e-3f);
-    const float nfx = (b[0] * b[4] - b[1] * b[3]) * det_inv;
-    const float nfy = (b[2] * b[3] - b[1] * b[4]) * det_inv;
-    const size_t o = (size_t)y * pitch + x;
-    fxp.p[o] = nfx;
-    fyp.p[o] = nfy;
-    if (rebuild) {
-        float m[5];
-        update_matrices_px(x, y, w, h, pitch, nfx, nfy, R0, R1, m);
+            for (int j = 1; j <= HALF; ++j) acc = acc + (row[-j] + row[j]);
+            b[k] = acc * area_inv;
+        }
+        // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
+        const float det_inv = f_rcp(b[0] * b[2] - b[1] * b[1] + 1e-3f);
+        const float nfx = (b[0] * b[4] - b[1] * b[3]) * det_inv;
+        const float nfy = (b[2] * b[3] - b[1] * b[4]) * det_inv;
+        const size_t o = (size_t)y * pitch + x;
+        fxp.p[o] = nfx;
+        fyp.p[o] = nfy;
+        if (rebuild) {
+            float m[5];
+            update_matrices_px(x, y, w, h, pitch, nfx, nfy, R0, R1, m);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) Mout.p[k][o] = m[k];
+            for (int k = 0; k < 5; ++k) Mout.p[k][o] = m[k];
+        }
     }
 }
+constexpr size_t kBoxSmemBytes = (size_t)(5 * (BH + 12) * (BW + 12) + 5 * BH * (BW + 12)) * sizeof(float);
 
 struct FarnParams {
     int num_levels = 5;
@@ -353,14 +368,16 @@ class Farneback final : public FlowAlgorithm {
         DFB_CUDA(cudaSetDevice(device_));
         pitch0_ = round_up(max_w_, 32);
         plane_elems_ = (size_t)pitch0_ * (max_h_ + 1);
-        // frames (fp32, per slot), work planes: blurred, level image, R0[5], R1[5], M[5] x2, flow x/y x2 (cur + prev level)
-        const int n_work = 2 + 10 + 10 + 4;
-        slab_.reserve((kInitialSlots + n_work) * Slab::padded(plane_elems_, 4) + (1 << 12));
-        for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(plane_elems_));
+        // a frame slot holds the polynomial expansion of every level (5 planes each): everything that depends on
+        // one frame only, so a frame shared by two consecutive pairs is blurred / resized / expanded once
+        LevelSet ls = levels_for(max_w_, max_h_, /*max_depth=*/true);
+        slot_elems_ = ls.total_r_elems;
+        const int n_work = 3 /*frame, blurred, img*/ + 10 /*M x2*/ + 4 /*flow x/y, cur + prev level*/;
+        slab_.reserve(kInitialSlots * Slab::padded(slot_elems_, 4) + n_work * Slab::padded(plane_elems_, 4) + (1 << 12));
+        for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(slot_elems_));
+        frame_ = slab_.take<float>(plane_elems_);
         blurred_ = slab_.take<float>(plane_elems_);
         img_ = slab_.take<float>(plane_elems_);
-        for (int k = 0; k < 5; ++k) R_[0][k] = slab_.take<float>(plane_elems_);
-        for (int k = 0; k < 5; ++k) R_[1][k] = slab_.take<float>(plane_elems_);
         for (int b = 0; b < 2; ++b)
             for (int k = 0; k < 5; ++k) M_[b][k] = slab_.take<float>(plane_elems_);
         for (int b = 0; b < 2; ++b) {
@@ -369,6 +386,7 @@ class Farneback final : public FlowAlgorithm {
         }
         slab_.zero();
         DFB_CUDA(cudaFuncSetAttribute(k_gauss_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, GT * (GT + 2 * kMaxHalf) * 4));
+        DFB_CUDA(cudaFuncSetAttribute(k_box_solve_update<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBoxSmemBytes));
     }
     ~Farneback() override {
         cudaSetDevice(device_);
@@ -379,16 +397,17 @@ class Farneback final : public FlowAlgorithm {
     void ensure_slots(int n) override {
         while ((int)slots_.size() < n) {
             float *p = nullptr;
-            DFB_CUDA(cudaMalloc(&p, plane_elems_ * sizeof(float)));
+            DFB_CUDA(cudaMalloc(&p, slot_elems_ * sizeof(float)));
+            DFB_CUDA(cudaMemset(p, 0, slot_elems_ * sizeof(float)));
             extra_slots_.push_back(p);
             slots_.push_back(p);
         }
     }
     bool set_param(const std::string &k, double v) override {
-        if (k == "num_levels") { if (v < 0 || v > kMaxLevels - 1) return false; prm_.num_levels = (int)v; }
-        else if (k == "pyr_scale") { if (!(v > 0 && v < 1)) return false; prm_.pyr_scale = v; }
+        if (k == "num_levels") { if (v < 0 || v > 5) return false; prm_.num_levels = (int)v; }
         else if (k == "num_iters") { if (v < 1) return false; prm_.num_iters = (int)v; }
         else if (k == "poly_sigma") prm_.poly_sigma = v;
+        else if (k == "pyr_scale") return v == 0.5;  // level geometry and the slot layout assume the default
         else if (k == "win_size" || k == "poly_n") return (k == "win_size" ? v == 13 : v == 5);  // compiled-in stencils
         else return false;
         return true;
@@ -404,92 +423,122 @@ class Farneback final : public FlowAlgorithm {
         return true;
     }
 
-    // per-frame work: u8 -> fp32 (the pyramid depends on the level's blur of the FULL-res frame, B.2, so it is built in solve)
+    // per-frame work (B.2, B.3): u8 -> fp32, then for every level: Gaussian blur of the FULL-resolution frame,
+    // bilinear resize to the level, polynomial expansion into the slot's R planes
     void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) override {
-        launch_u8_to_f32(src, pitch_bytes, Plane{slots_.at(slot), w, h, round_up(w, 32)}, s);
+        const LevelSet ls = levels_for(w, h, false);
+        const int pitch_full = round_up(w, 32);
+        const Plane frame{frame_, w, h, pitch_full};
+        launch_u8_to_f32(src, pitch_bytes, frame, s);
         ++launches;
+        const FarnConsts pc = poly_constants(prm_.poly_n, prm_.poly_sigma);
+        for (int l = 0; l < ls.n; ++l) {
+            const Level &L = ls.lv[l];
+            const GaussKernel gk = gaussian_kernel(L.smooth, L.sigma);
+            if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
+            const Plane blurred{blurred_, w, h, pitch_full};
+            k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame, blurred, gk);
+            DFB_KERNEL_CHECK();
+            const Plane img{img_, L.w, L.h, L.pitch};
+            const float rfx = (float)(1.0 / ((double)L.w / (double)w)), rfy = (float)(1.0 / ((double)L.h / (double)h));
+            launch_resize_linear(blurred, img, rfx, rfy, 1.0f, s);
+            k_poly_exp<5><<<dim3(ceil_div(L.w, PT), ceil_div(L.h, PT)), 256, 0, s>>>(img, r_planes(slot, L), pc);
+            DFB_KERNEL_CHECK();
+            launches += 3;
+        }
     }
 
+    // per-pair work (B.4, B.5): coarse -> fine, 10 fused box / solve / rebuild iterations per level
     void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes, cudaStream_t s) override {
-        const FarnConsts pc = poly_constants(prm_.poly_n, prm_.poly_sigma);
-        // B.1 level list
-        int cropped = 0;
-        double scale = 1.0;
-        for (; cropped < prm_.num_levels; ++cropped) {
-            scale *= prm_.pyr_scale;
-            if (w * scale < 32 || h * scale < 32) break;
-        }
-        const int pitch_full = round_up(w, 32);
-        const Plane frame[2] = {Plane{slots_.at(slot_a), w, h, pitch_full}, Plane{slots_.at(slot_b), w, h, pitch_full}};
-        int cur = 0, pw = 0, ph = 0, ppitch = 0;
-        bool have_prev = false;
-        for (int k = cropped; k >= 0; --k) {
-            scale = 1.0;
-            for (int i = 0; i < k; ++i) scale *= prm_.pyr_scale;
-            const double sigma = (1. / scale - 1) * 0.5;
-            int smooth = cv_round(sigma * 5) | 1;
-            smooth = std::max(smooth, 3);
-            const int W = cv_round(w * scale), H = cv_round(h * scale), pitch = round_up(W, 32);
-            const Plane fx{fx_[cur], W, H, pitch}, fy{fy_[cur], W, H, pitch};
-            if (!have_prev) {
+        const LevelSet ls = levels_for(w, h, false);
+        int cur = 0;
+        for (int l = 0; l < ls.n; ++l) {
+            const Level &L = ls.lv[l];
+            const Plane fx{fx_[cur], L.w, L.h, L.pitch}, fy{fy_[cur], L.w, L.h, L.pitch};
+            if (l == 0) {
                 launch_fill(fx, 0.f, s);
                 launch_fill(fy, 0.f, s);
-                launches += 2;
             } else {
-                const float rfx = (float)(1.0 / ((double)W / (double)pw)), rfy = (float)(1.0 / ((double)H / (double)ph));
+                const Level &Pv = ls.lv[l - 1];
+                const float rfx = (float)(1.0 / ((double)L.w / (double)Pv.w)), rfy = (float)(1.0 / ((double)L.h / (double)Pv.h));
                 const float mul = (float)(1.0 / prm_.pyr_scale);
-                launch_resize_linear(Plane{fx_[cur ^ 1], pw, ph, ppitch}, fx, rfx, rfy, mul, s);
-                launch_resize_linear(Plane{fy_[cur ^ 1], pw, ph, ppitch}, fy, rfx, rfy, mul, s);
-                launches += 2;
+                launch_resize_linear(Plane{fx_[cur ^ 1], Pv.w, Pv.h, Pv.pitch}, fx, rfx, rfy, mul, s);
+                launch_resize_linear(Plane{fy_[cur ^ 1], Pv.w, Pv.h, Pv.pitch}, fy, rfx, rfy, mul, s);
             }
-            Plane5 R[2];
-            const GaussKernel gk = gaussian_kernel(smooth, sigma);
-            if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
-            for (int i = 0; i < 2; ++i) {
-                const Plane blurred{blurred_, w, h, pitch_full};
-                k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame[i], blurred, gk);
-                DFB_KERNEL_CHECK();
-                const Plane img{img_, W, H, pitch};
-                const float rfx = (float)(1.0 / ((double)W / (double)w)), rfy = (float)(1.0 / ((double)H / (double)h));
-                launch_resize_linear(blurred, img, rfx, rfy, 1.0f, s);
-                R[i] = Plane5{{R_[i][0], R_[i][1], R_[i][2], R_[i][3], R_[i][4]}, W, H, pitch};
-                k_poly_exp<5><<<dim3(ceil_div(W, PT), ceil_div(H, PT)), 256, 0, s>>>(img, R[i], pc);
-                DFB_KERNEL_CHECK();
-                launches += 3;
-            }
+            launches += 2;
+            const Plane5 R0 = r_planes(slot_a, L), R1 = r_planes(slot_b, L);
             int mb = 0;
-            Plane5 M[2] = {Plane5{{M_[0][0], M_[0][1], M_[0][2], M_[0][3], M_[0][4]}, W, H, pitch},
-                           Plane5{{M_[1][0], M_[1][1], M_[1][2], M_[1][3], M_[1][4]}, W, H, pitch}};
-            k_update_matrices<<<dim3(ceil_div(W, 32), ceil_div(H, 8)), dim3(32, 8), 0, s>>>(fx, fy, R[0], R[1], M[mb]);
+            Plane5 M[2] = {Plane5{{M_[0][0], M_[0][1], M_[0][2], M_[0][3], M_[0][4]}, L.w, L.h, L.pitch},
+                           Plane5{{M_[1][0], M_[1][1], M_[1][2], M_[1][3], M_[1][4]}, L.w, L.h, L.pitch}};
+            k_update_matrices<<<dim3(ceil_div(L.w, 32), ceil_div(L.h, 8)), dim3(32, 8), 0, s>>>(fx, fy, R0, R1, M[mb]);
             DFB_KERNEL_CHECK();
             ++launches;
             for (int it = 0; it < prm_.num_iters; ++it) {
                 const int rebuild = it < prm_.num_iters - 1;
-                k_box_solve_update<6><<<dim3(ceil_div(W, BW), ceil_div(H, BH)), dim3(BW, BH), 0, s>>>(M[mb], fx, fy, R[0], R[1], M[mb ^ 1], rebuild);
+                k_box_solve_update<6><<<dim3(ceil_div(L.w, BW), ceil_div(L.h, BH)), 256, kBoxSmemBytes, s>>>(M[mb], fx, fy, R0, R1, M[mb ^ 1], rebuild);
                 DFB_KERNEL_CHECK();
                 ++launches;
                 mb ^= 1;
             }
-            have_prev = true;
-            pw = W;
-            ph = H;
-            ppitch = pitch;
             cur ^= 1;
         }
-        // last processed level is full resolution (k = 0): merge
-        launch_merge_flow(Plane{fx_[cur ^ 1], w, h, pitch_full}, Plane{fy_[cur ^ 1], w, h, pitch_full}, flow_xy, flow_pitch_bytes, s);
+        const Level &F = ls.lv[ls.n - 1];  // last processed level is full resolution (k = 0)
+        launch_merge_flow(Plane{fx_[cur ^ 1], F.w, F.h, F.pitch}, Plane{fy_[cur ^ 1], F.w, F.h, F.pitch}, flow_xy, flow_pitch_bytes, s);
         ++launches;
     }
 
   private:
+    struct Level {
+        int w, h, pitch, smooth;
+        double sigma;
+        size_t r_off;  // offset of this level's first R plane inside a slot (elements)
+    };
+    struct LevelSet {
+        int n = 0;
+        Level lv[kMaxLevels];
+        size_t total_r_elems = 0;
+    };
+    // B.1 level list in processing order (coarsest first)
+    LevelSet levels_for(int w, int h, bool max_depth) const {
+        LevelSet ls;
+        const int depth = max_depth ? 5 : prm_.num_levels;
+        int cropped = 0;
+        double scale = 1.0;
+        for (; cropped < depth; ++cropped) {
+            scale *= prm_.pyr_scale;
+            if (w * scale < 32 || h * scale < 32) break;
+        }
+        size_t off = 0;
+        for (int k = cropped; k >= 0; --k) {
+            scale = 1.0;
+            for (int i = 0; i < k; ++i) scale *= prm_.pyr_scale;
+            Level L;
+            L.sigma = (1. / scale - 1) * 0.5;
+            L.smooth = std::max(cv_round(L.sigma * 5) | 1, 3);
+            L.w = cv_round(w * scale);
+            L.h = cv_round(h * scale);
+            L.pitch = round_up(L.w, 32);
+            L.r_off = off;
+            off += 5 * (((size_t)L.pitch * (L.h + 1) + 63) & ~size_t(63));
+            ls.lv[ls.n++] = L;
+        }
+        ls.total_r_elems = off;
+        return ls;
+    }
+    Plane5 r_planes(int slot, const Level &L) const {
+        float *base = slots_.at(slot) + L.r_off;
+        const size_t pe = ((size_t)L.pitch * (L.h + 1) + 63) & ~size_t(63);
+        return Plane5{{base, base + pe, base + 2 * pe, base + 3 * pe, base + 4 * pe}, L.w, L.h, L.pitch};
+    }
+
     static constexpr int kInitialSlots = 4;
     int device_, max_w_, max_h_, pitch0_ = 0;
-    size_t plane_elems_ = 0;
+    size_t plane_elems_ = 0, slot_elems_ = 0;
     FarnParams prm_;
     Slab slab_;
     std::vector<float *> slots_, extra_slots_;
-    float *blurred_ = nullptr, *img_ = nullptr;
-    float *R_[2][5] = {}, *M_[2][5] = {};
+    float *frame_ = nullptr, *blurred_ = nullptr, *img_ = nullptr;
+    float *M_[2][5] = {};
     float *fx_[2] = {}, *fy_[2] = {};
 };
 

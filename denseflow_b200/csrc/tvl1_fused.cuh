@@ -47,7 +47,7 @@ struct FusedJob {
 // Several independent pairs ("lanes") per launch: lane i is solved by CTAs [i*group, (i+1)*group) with
 // their own barrier words, partials and workspace.  Coarse pyramid levels have fewer tiles than the
 // GPU has SMs; running pairs side by side keeps every SM busy without touching a pair's arithmetic.
-constexpr int kFusedMaxLanes = 8;
+constexpr int kFusedMaxLanes = 16;  // 16 jobs x ~1.4 KB of kernel parameters (limit 32 KB since CUDA 12.1)
 constexpr int kFusedMapsPerLevel = 8;
 constexpr int kTensorMapBytes = 128;  // sizeof(CUtensorMap)
 struct FusedBatch {

@@ -60,3 +60,12 @@ def test_farneback_720p_config(oracle):
     ref = oracle.farn_calc(fr[0], fr[1])
     flow = _engine(1280, 720).calc(fr[0], fr[1])
     assert synth.aee(flow, ref) <= AEE_TOL
+
+
+def test_farneback_1080p_six_levels(oracle):
+    """1920x1080 keeps the k = 5 level (60 x 34): smoothSize 79, the widest Gaussian of the path."""
+    assert oracle.farn_levels(1920, 1080)[0][:3] == (60, 34, 79)
+    fr = synth.stream(1080, 1920, 2, seed=1)
+    ref = oracle.farn_calc(fr[0], fr[1])
+    flow = _engine(1920, 1080).calc(fr[0], fr[1])
+    assert synth.aee(flow, ref) <= AEE_TOL
