@@ -176,7 +176,24 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     m[4] = r6 * r2 + r5 * r3;
 }
 
-__global__ void __launch_bounds__(256) k_update_matrices(Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 M) {
+// Several independent pairs per launch (blockIdx.z = pair): the coarse levels are far too small to fill 148 SMs and
+// every kernel of the iteration is latency-bound there, so pairs are solved side by side (same idea as the TV-L1 lanes).
+constexpr int kMaxFarnBatch = 8;
+struct PairArgs {
+    Plane5 R0, R1, M[2];
+    Plane fx, fy;    // this level's flow
+    Plane pfx, pfy;  // previous (coarser) level's flow
+    float *flow_xy;
+    size_t flow_pitch_bytes;
+};
+struct FarnBatchArgs {
+    PairArgs p[kMaxFarnBatch];
+};
+
+__global__ void __launch_bounds__(256) k_update_matrices(const __grid_constant__ FarnBatchArgs args, int mb) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const Plane fxp = a.fx, fyp = a.fy;
+    const Plane5 R0 = a.R0, R1 = a.R1, M = a.M[mb];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= M.w || y >= M.h) return;
     const size_t o = (size_t)y * M.pitch + x;
@@ -195,8 +212,10 @@ __global__ void __launch_bounds__(256) k_update_matrices(Plane fxp, Plane fyp, P
 constexpr int BW = 32, BH = 32;
 
 template <int HALF>
-__global__ void __launch_bounds__(256) k_box_solve_update(Plane5 Min, Plane fxp, Plane fyp, Plane5 R0, Plane5 R1, Plane5 Mout,
-                                                           int rebuild) {
+__global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const Plane5 Min = a.M[mb], Mout = a.M[mb ^ 1], R0 = a.R0, R1 = a.R1;
+    const Plane fxp = a.fx, fyp = a.fy;
     constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
     extern __shared__ float box_smem[];
     float(*raw)[sh][sw] = reinterpret_cast<float(*)[sh][sw]>(box_smem);               // [5][sh][sw]
@@ -213,48 +232,120 @@ __global__ void __launch_bounds__(256) k_box_solve_update(Plane5 Min, Plane fxp,
         for (int k = 0; k < 5; ++k) raw[k][ty][tx] = Min.p[k][o];
     }
     __syncthreads();
-    // vertical sums.  Clamped rows are materialised in the window, except that the reference clamps the row index
-    // of the TAP (max(y-j,0), min(y+j,h-1)) — identical, because the window rows are themselves clamped copies.
-    for (int i = tid; i < BH * sw; i += 256) {
-        const int ty = i / sw, tx = i - ty * sw;
+    // vertical sums, register-blocked: one task = 4 vertically consecutive outputs of one column and plane
+    // (16 window reads for 4 sums instead of 52); each sum keeps the reference's order (centre, then symmetric
+    // pairs outward).  Clamped rows are materialised in the window, which equals clamping the tap's row index.
+    constexpr int VG = 4;
+    for (int i = tid; i < 5 * (BH / VG) * sw; i += 256) {
+        const int tx = i % sw, rest = i / sw;
+        const int g = rest % (BH / VG), k = rest / (BH / VG);
+        float v[VG + 2 * HALF];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            float acc = raw[k][ty + HALF][tx];
+        for (int q = 0; q < VG + 2 * HALF; ++q) v[q] = raw[k][g * VG + q][tx];
 #pragma unroll
-            for (int j = 1; j <= HALF; ++j) acc = acc + (raw[k][ty + HALF - j][tx] + raw[k][ty + HALF + j][tx]);
-            vs[k][ty][tx] = acc;
+        for (int o = 0; o < VG; ++o) {
+            float acc = v[o + HALF];
+#pragma unroll
+            for (int j = 1; j <= HALF; ++j) acc = acc + (v[o + HALF - j] + v[o + HALF + j]);
+            vs[k][g * VG + o][tx] = acc;
         }
     }
     __syncthreads();
+    // horizontal sums + solve + rebuild: each thread owns 4 consecutive pixels of one row (16-float window per plane)
     constexpr float area_inv = 1.f / (float)((1 + 2 * HALF) * (1 + 2 * HALF));
-    for (int i = tid; i < BH * BW; i += 256) {
-        const int ty = i / BW, tx = i - ty * BW;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= w || y >= h) continue;
-        float b[5];
+    static_assert(BW * BH == 256 * 4 && BW % 4 == 0 && (BW + 2 * HALF) % 4 == 0, "one pass, float4-aligned rows");
+    {
+        const int ty = tid / (BW / 4), tx0 = (tid % (BW / 4)) * 4;
+        const int y = y0 + ty;
+        float b[4][5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const float *row = &vs[k][ty][tx + HALF];
-            float acc = row[0];
+            float v[4 + 2 * HALF];
 #pragma unroll
-            for (int j = 1; j <= HALF; ++j) acc = acc + (row[-j] + row[j]);
-            b[k] = acc * area_inv;
+            for (int q = 0; q < (4 + 2 * HALF) / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4 *>(&vs[k][ty][tx0 + 4 * q]);
+                v[4 * q] = t.x;
+                v[4 * q + 1] = t.y;
+                v[4 * q + 2] = t.z;
+                v[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float acc = v[o + HALF];
+#pragma unroll
+                for (int j = 1; j <= HALF; ++j) acc = acc + (v[o + HALF - j] + v[o + HALF + j]);
+                b[o][k] = acc * area_inv;
+            }
         }
-        // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
-        const float det_inv = f_rcp(b[0] * b[2] - b[1] * b[1] + 1e-3f);
-        const float nfx = (b[0] * b[4] - b[1] * b[3]) * det_inv;
-        const float nfy = (b[2] * b[3] - b[1] * b[4]) * det_inv;
-        const size_t o = (size_t)y * pitch + x;
-        fxp.p[o] = nfx;
-        fyp.p[o] = nfy;
-        if (rebuild) {
-            float m[5];
-            update_matrices_px(x, y, w, h, pitch, nfx, nfy, R0, R1, m);
+        // all four pixels' gathers are issued before any of them is consumed: coordinates are clamped into the image
+        // (safe reads), only the stores are predicated
+        const int yc = min(y, h - 1);
+        float nfx[4], nfy[4], m[4][5];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) Mout.p[k][o] = m[k];
+        for (int o = 0; o < 4; ++o) {
+            // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
+            const float det_inv = f_rcp(b[o][0] * b[o][2] - b[o][1] * b[o][1] + 1e-3f);
+            nfx[o] = (b[o][0] * b[o][4] - b[o][1] * b[o][3]) * det_inv;
+            nfy[o] = (b[o][2] * b[o][3] - b[o][1] * b[o][4]) * det_inv;
+        }
+        if (rebuild) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) update_matrices_px(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], R0, R1, m[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int x = x0 + tx0 + o;
+            if (x < w && y < h) {
+                const size_t oo = (size_t)y * pitch + x;
+                fxp.p[oo] = nfx[o];
+                fyp.p[oo] = nfy[o];
+                if (rebuild) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) Mout.p[k][oo] = m[o][k];
+                }
+            }
         }
     }
 }
+// level start: flow = 0 at the coarsest level, else resize(prev) * (1/pyrScale) (B.2), both components, batched
+__global__ void __launch_bounds__(256) k_flow_init(const __grid_constant__ FarnBatchArgs args, int first, float rfx, float rfy, float mul) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= a.fx.w || dy >= a.fx.h) return;
+    const size_t o = (size_t)dy * a.fx.pitch + dx;
+    if (first) {
+        a.fx.p[o] = 0.f;
+        a.fy.p[o] = 0.f;
+        return;
+    }
+    const Plane s1 = a.pfx, s2 = a.pfy;
+    const float sx = dx * rfx, sy = dy * rfy;
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const size_t r1 = (size_t)min(y1, s1.h - 1) * s1.pitch, r2 = (size_t)min(y2, s1.h - 1) * s1.pitch;
+    const int x1r = min(x1, s1.w - 1), x2r = min(x2, s1.w - 1);
+    const float w11 = (x2 - sx) * (y2 - sy), w12 = (sx - x1) * (y2 - sy), w21 = (x2 - sx) * (sy - y1), w22 = (sx - x1) * (sy - y1);
+    float o1 = 0.f, o2 = 0.f;
+    o1 = o1 + s1.p[r1 + x1r] * w11;
+    o1 = o1 + s1.p[r1 + x2r] * w12;
+    o1 = o1 + s1.p[r2 + x1r] * w21;
+    o1 = o1 + s1.p[r2 + x2r] * w22;
+    o2 = o2 + s2.p[r1 + x1r] * w11;
+    o2 = o2 + s2.p[r1 + x2r] * w12;
+    o2 = o2 + s2.p[r2 + x1r] * w21;
+    o2 = o2 + s2.p[r2 + x2r] * w22;
+    a.fx.p[o] = o1 * mul;
+    a.fy.p[o] = o2 * mul;
+}
+
+__global__ void __launch_bounds__(256) k_farn_merge(const __grid_constant__ FarnBatchArgs args) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.fx.w || y >= a.fx.h) return;
+    float2 *row = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.flow_xy) + (size_t)y * a.flow_pitch_bytes);
+    row[x] = make_float2(a.fx.p[(size_t)y * a.fx.pitch + x], a.fy.p[(size_t)y * a.fy.pitch + x]);
+}
+
 constexpr size_t kBoxSmemBytes = (size_t)(5 * (BH + 12) * (BW + 12) + 5 * BH * (BW + 12)) * sizeof(float);
 
 struct FarnParams {
@@ -372,25 +463,21 @@ class Farneback final : public FlowAlgorithm {
         // one frame only, so a frame shared by two consecutive pairs is blurred / resized / expanded once
         LevelSet ls = levels_for(max_w_, max_h_, /*max_depth=*/true);
         slot_elems_ = ls.total_r_elems;
-        const int n_work = 3 /*frame, blurred, img*/ + 10 /*M x2*/ + 4 /*flow x/y, cur + prev level*/;
+        const int n_work = 3 /*frame, blurred, img*/;
         slab_.reserve(kInitialSlots * Slab::padded(slot_elems_, 4) + n_work * Slab::padded(plane_elems_, 4) + (1 << 12));
         for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(slot_elems_));
         frame_ = slab_.take<float>(plane_elems_);
         blurred_ = slab_.take<float>(plane_elems_);
         img_ = slab_.take<float>(plane_elems_);
-        for (int b = 0; b < 2; ++b)
-            for (int k = 0; k < 5; ++k) M_[b][k] = slab_.take<float>(plane_elems_);
-        for (int b = 0; b < 2; ++b) {
-            fx_[b] = slab_.take<float>(plane_elems_);
-            fy_[b] = slab_.take<float>(plane_elems_);
-        }
         slab_.zero();
+        ensure_lanes(1);
         DFB_CUDA(cudaFuncSetAttribute(k_gauss_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, GT * (GT + 2 * kMaxHalf) * 4));
         DFB_CUDA(cudaFuncSetAttribute(k_box_solve_update<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBoxSmemBytes));
     }
     ~Farneback() override {
         cudaSetDevice(device_);
         for (auto p : extra_slots_) cudaFree(p);
+        for (auto &l : lanes_) cudaFree(l.own);
     }
     const char *name() const override { return "farn"; }
     int num_slots() const override { return (int)slots_.size(); }
@@ -450,41 +537,64 @@ class Farneback final : public FlowAlgorithm {
 
     // per-pair work (B.4, B.5): coarse -> fine, 10 fused box / solve / rebuild iterations per level
     void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes, cudaStream_t s) override {
+        const PairJob one{slot_a, slot_b, flow_xy, flow_pitch_bytes};
+        solve_batch(&one, 1, w, h, s);
+    }
+    int max_concurrent_pairs(int, int) override { return kMaxFarnBatch; }
+
+    void solve_batch(const PairJob *jobs, int count, int w, int h, cudaStream_t s) override {
         const LevelSet ls = levels_for(w, h, false);
-        int cur = 0;
-        for (int l = 0; l < ls.n; ++l) {
-            const Level &L = ls.lv[l];
-            const Plane fx{fx_[cur], L.w, L.h, L.pitch}, fy{fy_[cur], L.w, L.h, L.pitch};
-            if (l == 0) {
-                launch_fill(fx, 0.f, s);
-                launch_fill(fy, 0.f, s);
-            } else {
-                const Level &Pv = ls.lv[l - 1];
-                const float rfx = (float)(1.0 / ((double)L.w / (double)Pv.w)), rfy = (float)(1.0 / ((double)L.h / (double)Pv.h));
-                const float mul = (float)(1.0 / prm_.pyr_scale);
-                launch_resize_linear(Plane{fx_[cur ^ 1], Pv.w, Pv.h, Pv.pitch}, fx, rfx, rfy, mul, s);
-                launch_resize_linear(Plane{fy_[cur ^ 1], Pv.w, Pv.h, Pv.pitch}, fy, rfx, rfy, mul, s);
-            }
-            launches += 2;
-            const Plane5 R0 = r_planes(slot_a, L), R1 = r_planes(slot_b, L);
-            int mb = 0;
-            Plane5 M[2] = {Plane5{{M_[0][0], M_[0][1], M_[0][2], M_[0][3], M_[0][4]}, L.w, L.h, L.pitch},
-                           Plane5{{M_[1][0], M_[1][1], M_[1][2], M_[1][3], M_[1][4]}, L.w, L.h, L.pitch}};
-            k_update_matrices<<<dim3(ceil_div(L.w, 32), ceil_div(L.h, 8)), dim3(32, 8), 0, s>>>(fx, fy, R0, R1, M[mb]);
-            DFB_KERNEL_CHECK();
-            ++launches;
-            for (int it = 0; it < prm_.num_iters; ++it) {
-                const int rebuild = it < prm_.num_iters - 1;
-                k_box_solve_update<6><<<dim3(ceil_div(L.w, BW), ceil_div(L.h, BH)), 256, kBoxSmemBytes, s>>>(M[mb], fx, fy, R0, R1, M[mb ^ 1], rebuild);
+        for (int j0 = 0; j0 < count; j0 += kMaxFarnBatch) {
+            const int nb = std::min(kMaxFarnBatch, count - j0);
+            ensure_lanes(nb);
+            int cur = 0;
+            FarnBatchArgs args{};
+            for (int l = 0; l < ls.n; ++l) {
+                const Level &L = ls.lv[l];
+                for (int i = 0; i < nb; ++i) {
+                    const Lane &ln = lanes_[i];
+                    PairArgs &a = args.p[i];
+                    a.R0 = r_planes(jobs[j0 + i].slot_a, L);
+                    a.R1 = r_planes(jobs[j0 + i].slot_b, L);
+                    for (int b = 0; b < 2; ++b)
+                        a.M[b] = Plane5{{ln.M[b][0], ln.M[b][1], ln.M[b][2], ln.M[b][3], ln.M[b][4]}, L.w, L.h, L.pitch};
+                    a.fx = Plane{ln.fx[cur], L.w, L.h, L.pitch};
+                    a.fy = Plane{ln.fy[cur], L.w, L.h, L.pitch};
+                    if (l > 0) {
+                        const Level &Pv = ls.lv[l - 1];
+                        a.pfx = Plane{ln.fx[cur ^ 1], Pv.w, Pv.h, Pv.pitch};
+                        a.pfy = Plane{ln.fy[cur ^ 1], Pv.w, Pv.h, Pv.pitch};
+                    }
+                    a.flow_xy = jobs[j0 + i].flow_xy;
+                    a.flow_pitch_bytes = jobs[j0 + i].flow_pitch_bytes;
+                }
+                const dim3 g8(ceil_div(L.w, 32), ceil_div(L.h, 8), nb), b8(32, 8);
+                float rfx = 1.f, rfy = 1.f;
+                if (l > 0) {
+                    rfx = (float)(1.0 / ((double)L.w / (double)ls.lv[l - 1].w));
+                    rfy = (float)(1.0 / ((double)L.h / (double)ls.lv[l - 1].h));
+                }
+                k_flow_init<<<g8, b8, 0, s>>>(args, l == 0, rfx, rfy, (float)(1.0 / prm_.pyr_scale));
                 DFB_KERNEL_CHECK();
-                ++launches;
-                mb ^= 1;
+                int mb = 0;
+                k_update_matrices<<<g8, b8, 0, s>>>(args, mb);
+                DFB_KERNEL_CHECK();
+                launches += 2;
+                for (int it = 0; it < prm_.num_iters; ++it) {
+                    const int rebuild = it < prm_.num_iters - 1;
+                    k_box_solve_update<6><<<dim3(ceil_div(L.w, BW), ceil_div(L.h, BH), nb), 256, kBoxSmemBytes, s>>>(args, mb, rebuild);
+                    DFB_KERNEL_CHECK();
+                    ++launches;
+                    mb ^= 1;
+                }
+                if (l == ls.n - 1) {  // last processed level is full resolution (k = 0): merge -> CV_32FC2
+                    k_farn_merge<<<g8, b8, 0, s>>>(args);
+                    DFB_KERNEL_CHECK();
+                    ++launches;
+                }
+                cur ^= 1;
             }
-            cur ^= 1;
         }
-        const Level &F = ls.lv[ls.n - 1];  // last processed level is full resolution (k = 0)
-        launch_merge_flow(Plane{fx_[cur ^ 1], F.w, F.h, F.pitch}, Plane{fy_[cur ^ 1], F.w, F.h, F.pitch}, flow_xy, flow_pitch_bytes, s);
-        ++launches;
     }
 
   private:
@@ -538,8 +648,34 @@ class Farneback final : public FlowAlgorithm {
     Slab slab_;
     std::vector<float *> slots_, extra_slots_;
     float *frame_ = nullptr, *blurred_ = nullptr, *img_ = nullptr;
-    float *M_[2][5] = {};
-    float *fx_[2] = {}, *fy_[2] = {};
+    // per-pair workspace: M (two buffers of five planes) and the flow of the current + previous level
+    struct Lane {
+        float *own = nullptr;
+        float *M[2][5] = {};
+        float *fx[2] = {}, *fy[2] = {};
+    };
+    std::vector<Lane> lanes_;
+    void ensure_lanes(int n) {
+        while ((int)lanes_.size() < n) {
+            Lane l;
+            const size_t pl = Slab::padded(plane_elems_, 4) / sizeof(float);
+            DFB_CUDA(cudaMalloc(&l.own, 14 * pl * sizeof(float)));
+            DFB_CUDA(cudaMemset(l.own, 0, 14 * pl * sizeof(float)));
+            float *c = l.own;
+            for (int b = 0; b < 2; ++b)
+                for (int k = 0; k < 5; ++k) {
+                    l.M[b][k] = c;
+                    c += pl;
+                }
+            for (int b = 0; b < 2; ++b) {
+                l.fx[b] = c;
+                c += pl;
+                l.fy[b] = c;
+                c += pl;
+            }
+            lanes_.push_back(l);
+        }
+    }
 };
 
 }  // namespace
