@@ -126,6 +126,36 @@ class DenseOpticalFlow:
                                                 qx.data_ptr(), qy.data_ptr(), w, C.c_void_p(s)))
         return qx, qy
 
+    # -- frame preparation (cvtColor BGR2GRAY + resize INTER_LINEAR, src/denseflow_gpu.cpp:163-170), bit-exact to OpenCV CPU --
+    def bgr_to_gray_device(self, bgr):
+        import torch
+        h, w = bgr.shape[:2]
+        gray = torch.empty((h, w), dtype=torch.uint8, device=bgr.device)
+        s = torch.cuda.current_stream(bgr.device).cuda_stream
+        self._check(self._L.dfb_bgr_to_gray_device(self._h, bgr.data_ptr(), bgr.stride(0), w, h, gray.data_ptr(), w, C.c_void_p(s)))
+        return gray
+
+    def resize_gray_device(self, gray, dst_width, dst_height):
+        import torch
+        h, w = gray.shape
+        out = torch.empty((dst_height, dst_width), dtype=torch.uint8, device=gray.device)
+        s = torch.cuda.current_stream(gray.device).cuda_stream
+        self._check(self._L.dfb_resize_gray_device(self._h, gray.data_ptr(), gray.stride(0), w, h, out.data_ptr(), dst_width,
+                                                   dst_width, dst_height, C.c_void_p(s)))
+        return out
+
+    # -- imencode(".jpg", plane) on the GPU (src/common.cpp:56-57), OpenCV default quality 95 --
+    def encode_jpeg_gray_device(self, gray, quality=95):
+        import torch
+        h, w = gray.shape
+        cap = self._L.dfb_jpeg_max_bytes(w, h)
+        buf = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        s = torch.cuda.current_stream(gray.device).cuda_stream
+        self._check(self._L.dfb_encode_jpeg_gray_device(self._h, gray.data_ptr(), gray.stride(0), w, h, int(quality), buf.ctypes.data,
+                                                        cap, C.byref(n), C.c_void_p(s)))
+        return buf[:n.value].tobytes()
+
     # -- counters for the roofline arithmetic --
     def tvl1_stats(self):
         st = _lib.Tvl1Stats()

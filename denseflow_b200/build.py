@@ -69,7 +69,7 @@ def build(variants=("default", "strict"), verbose=False, force=False):
                     print(log)
         out = os.path.join(LIBDIR, out_name)
         if jobs or not os.path.exists(out):
-            _run([NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+            _run([NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-cudart", "shared", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
         outs.append(out)
     return outs
 

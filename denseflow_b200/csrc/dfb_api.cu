@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "engine.h"
+#include "jpeg.h"
+#include "preproc.h"
 #include "tvl1.cuh"
 
 using namespace dfb;
@@ -34,6 +36,10 @@ struct dfb_handle {
     uint8_t *h_frame[kFrameRing] = {};
     float *h_flow[kFlowRing] = {};
     uint8_t *h_q[kFlowRing] = {};
+    // resize coefficient tables on the device, rebuilt when the geometry changes
+    std::unique_ptr<JpegEncoder> jpeg;  // created on first use
+    ResizeTap *d_taps = nullptr;
+    int taps_cap = 0, taps_sw = 0, taps_sh = 0, taps_dw = 0, taps_dh = 0;
 };
 
 namespace {
@@ -297,6 +303,8 @@ void dfb_destroy(dfb_handle *h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
+    h->jpeg.reset();
+    if (h->d_taps) cudaFree(h->d_taps);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -419,6 +427,77 @@ int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, 
         DFB_CUDA(cudaSetDevice(h->device));
         launch_quantise(flow_xy, flow_pitch, width, height, bound, qx, qy, q_pitch, static_cast<cudaStream_t>(stream));
         ++h->alg->launches;
+        return DFB_OK;
+    });
+}
+
+int dfb_bgr_to_gray_device(dfb_handle *h, const uint8_t *bgr, size_t bgr_pitch, int width, int height, uint8_t *gray,
+                           size_t gray_pitch, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!bgr || !gray) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (width <= 0 || height <= 0 || bgr_pitch < (size_t)width * 3 || gray_pitch < (size_t)width)
+        return fail(h, DFB_ERR_INVALID_ARG, "bad geometry");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        launch_bgr_to_gray(bgr, bgr_pitch, width, height, gray, gray_pitch, static_cast<cudaStream_t>(stream));
+        ++h->alg->launches;
+        return DFB_OK;
+    });
+}
+
+int dfb_resize_gray_device(dfb_handle *h, const uint8_t *src, size_t src_pitch, int sw, int sh, uint8_t *dst, size_t dst_pitch,
+                           int dw, int dh, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!src || !dst) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || src_pitch < (size_t)sw || dst_pitch < (size_t)dw)
+        return fail(h, DFB_ERR_INVALID_ARG, "bad geometry");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (sw == dw && sh == dh) {  // cv::resize with an equal size is a copy
+            DFB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, sw, sh, cudaMemcpyDeviceToDevice, s));
+            return DFB_OK;
+        }
+        if (h->taps_sw != sw || h->taps_sh != sh || h->taps_dw != dw || h->taps_dh != dh) {
+            std::vector<ResizeTap> xt, yt;
+            build_resize_taps(dw, sw, true, xt);
+            build_resize_taps(dh, sh, false, yt);
+            if (dw + dh > h->taps_cap) {
+                DFB_CUDA(cudaDeviceSynchronize());
+                if (h->d_taps) DFB_CUDA(cudaFree(h->d_taps));
+                h->taps_cap = dw + dh;
+                DFB_CUDA(cudaMalloc(&h->d_taps, sizeof(ResizeTap) * h->taps_cap));
+            } else {
+                DFB_CUDA(cudaDeviceSynchronize());  // a launch with the old tables may still be running
+            }
+            DFB_CUDA(cudaMemcpy(h->d_taps, xt.data(), sizeof(ResizeTap) * dw, cudaMemcpyHostToDevice));
+            DFB_CUDA(cudaMemcpy(h->d_taps + dw, yt.data(), sizeof(ResizeTap) * dh, cudaMemcpyHostToDevice));
+            h->taps_sw = sw;
+            h->taps_sh = sh;
+            h->taps_dw = dw;
+            h->taps_dh = dh;
+        }
+        launch_resize_u8(src, src_pitch, sw, sh, dst, dst_pitch, dw, dh, h->d_taps, h->d_taps + dw, s);
+        ++h->alg->launches;
+        return DFB_OK;
+    });
+}
+
+size_t dfb_jpeg_max_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    return (size_t)width * height * 2 + 4096;  // far above any baseline gray JPEG of this size
+}
+
+int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_pitch, int width, int height, int quality,
+                                uint8_t *out, size_t out_capacity, size_t *out_len, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!gray || !out || !out_len) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (width <= 0 || height <= 0 || gray_pitch < (size_t)width || quality < 1 || quality > 100)
+        return fail(h, DFB_ERR_INVALID_ARG, "bad geometry or quality");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        if (!h->jpeg) h->jpeg.reset(new JpegEncoder());
+        *out_len = h->jpeg->encode_gray(gray, gray_pitch, width, height, quality, out, out_capacity, static_cast<cudaStream_t>(stream));
         return DFB_OK;
     });
 }

@@ -76,7 +76,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "scale_step") { if (!(v > 0 && v < 1)) return false; prm_.scale_step = v; }
         else if (k == "fused") prm_.fused = v != 0;
         else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
-        else if (k == "flag_sync") prm_.flag_sync = v != 0;
+        else if (k == "flag_sync") prm_.flag_sync = (int)v;  // 0 CTA barriers, 1 spin on neighbour flags, n > 1: spin with n ns back-off
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "use_tma") prm_.use_tma = v != 0;
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }

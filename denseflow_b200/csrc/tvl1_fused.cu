@@ -232,8 +232,9 @@ __device__ __forceinline__ void phase_merge(const int G, const int bid, const Fu
 // the image is overwritten with a copy of the border pixel after every primal step, so the
 // difference is exactly 0 without per-pixel masking; only tiles touching that border pay for it.
 // Returns this thread's share of sum(diff) of the last primal step when `check`.
-__device__ __forceinline__ void wait_ge(const volatile int *flag, int v) {
+__device__ __forceinline__ void wait_ge(const volatile int *flag, int v, unsigned backoff_ns = 0) {
     while (*flag - v < 0) {
+        if (backoff_ns) __nanosleep(backoff_ns);  // a spinning warp competes for issue slots with the warps it waits for
     }
 }
 __device__ __forceinline__ void signal(volatile int *flag, int v) {
@@ -256,7 +257,8 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
     const int gy0 = ry0 + RPT * wq;
     const float taut = job.c.taut;
     volatile int *prog = sm.prog;
-    const bool flagsync = job.flag_sync != 0;  // 0: CTA-wide barriers between half-steps (debug / comparison)
+    const bool flagsync = job.flag_sync != 0;
+    const unsigned backoff = job.flag_sync > 1 ? (unsigned)job.flag_sync : 0u;  // 0: CTA-wide barriers between half-steps (debug / comparison)
 
     float4 p11[RPT], p12[RPT], p21[RPT], p22[RPT];
     const int so0 = (RPT * wq) * TW + 4 * lane;  // this thread's slot in row 0 of its warp (thread-private in smem planes)
@@ -334,7 +336,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         // p above the region's first row: the image border (p = 0) for tile row 0, halo garbage otherwise
         float4 up12 = zero4(), up22 = zero4();
         if (wq > 0) {
-            if (flagsync) wait_ge(&prog[wq - 1], base + 2 * it);
+            if (flagsync) wait_ge(&prog[wq - 1], base + 2 * it, backoff);
             up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
             up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
         }
@@ -396,7 +398,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
                 d1 = c1;  // region's last row: halo, or the mirrored image border
                 d2 = c2;
                 if (wq < kWarps - 1) {
-                    if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1);
+                    if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1, backoff);
                     if (!(edge_y && rbot == RPT - 1)) {
                         d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
                         d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);

@@ -111,6 +111,28 @@ int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, 
                         uint8_t *qx, uint8_t *qy, size_t q_pitch, void *stream);
 
 /*
+ * Frame preparation on device buffers — what the reference's decode stage does on the CPU to every
+ * frame before the hot path: cvtColor(frame, gray, COLOR_BGR2GRAY) src/denseflow_gpu.cpp:163 and
+ * cv::resize(gray, gray, new_size) [INTER_LINEAR] :166-170.  Both are bit-exact to OpenCV's CPU fixed-point
+ * arithmetic (the flow is computed on these pixels).  Pitches in bytes; bgr is packed 3 bytes per pixel.
+ */
+int dfb_bgr_to_gray_device(dfb_handle *h, const uint8_t *bgr, size_t bgr_pitch, int width, int height, uint8_t *gray,
+                           size_t gray_pitch, void *stream);
+int dfb_resize_gray_device(dfb_handle *h, const uint8_t *src, size_t src_pitch, int src_width, int src_height, uint8_t *dst,
+                           size_t dst_pitch, int dst_width, int dst_height, void *stream);
+
+/*
+ * JPEG-encode one uint8 plane that lives in device memory.  Replaces
+ * imencode(".jpg", flow_img_x, encoded_x) / (..., flow_img_y, ...)  src/common.cpp:56-57 with OpenCV's defaults when
+ * quality = 95 (baseline sequential, one gray component).  out is a host buffer of out_capacity bytes
+ * (dfb_jpeg_max_bytes(width, height) is always enough); *out_len receives the length.  Blocks until
+ * the bitstream is on the host.  Not byte-identical to libjpeg-turbo (lossy; the reference pins no bytes).
+ */
+size_t dfb_jpeg_max_bytes(int width, int height);
+int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_pitch, int width, int height, int quality,
+                                uint8_t *out, size_t out_capacity, size_t *out_len, void *stream);
+
+/*
  * Work counters of the most recent calc on this handle (for the roofline arithmetic):
  *   iters[nscales*warps] executed inner iterations per (scale, warp), index s*warps + w, s = 0 finest
  *   level_w/level_h[nscales] pyramid sizes
