@@ -156,6 +156,19 @@ class DenseOpticalFlow:
                                                         cap, C.byref(n), C.c_void_p(s)))
         return buf[:n.value].tobytes()
 
+    # -- test hook: one stand-alone kernel on host planes --
+    def debug_run_kernel(self, kernel, inputs, n_out, scalars=(), out_shape=None):
+        inputs = [np.ascontiguousarray(a, np.float32) for a in inputs]
+        h, w = inputs[0].shape
+        oshape = out_shape or (h, w)
+        outs = [np.empty(oshape, np.float32) for _ in range(n_out)]
+        ip = (C.c_void_p * len(inputs))(*[a.ctypes.data for a in inputs])
+        op = (C.c_void_p * n_out)(*[a.ctypes.data for a in outs])
+        sc = (C.c_double * max(len(scalars), 1))(*[float(x) for x in scalars])
+        so = (C.c_double * 1)(0.0)
+        self._check(self._L.dfb_debug_run_kernel(self._h, kernel.encode(), ip, len(inputs), op, n_out, w, h, sc, len(scalars), so))
+        return outs, so[0]
+
     # -- counters for the roofline arithmetic --
     def tvl1_stats(self):
         st = _lib.Tvl1Stats()

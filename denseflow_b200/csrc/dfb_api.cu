@@ -502,6 +502,87 @@ int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_
     });
 }
 
+int dfb_debug_run_kernel(dfb_handle *h, const char *kernel, const float *const *in, int n_in, float *const *out, int n_out, int width,
+                         int height, const double *scalars, int n_scalars, double *scalars_out) {
+    if (!h || !kernel) return DFB_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || n_in < 0 || n_out < 0 || n_in > 16 || n_out > 16) return fail(h, DFB_ERR_INVALID_ARG, "bad arguments");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        const std::string k(kernel);
+        auto sc = [&](int i) { return i < n_scalars ? scalars[i] : 0.0; };
+        int ow = width, oh = height;
+        if (k == "resize") {
+            ow = (int)sc(0);
+            oh = (int)sc(1);
+            if (ow <= 0 || oh <= 0) throw std::runtime_error("resize: bad destination size");
+        }
+        const int pitch = round_up(width, 32), opitch = round_up(ow, 32);
+        std::vector<float *> dev;
+        auto alloc = [&](int w_, int h_, int p_) {
+            float *p = nullptr;
+            DFB_CUDA(cudaMalloc(&p, (size_t)p_ * (h_ + 1) * sizeof(float)));
+            DFB_CUDA(cudaMemset(p, 0, (size_t)p_ * (h_ + 1) * sizeof(float)));
+            dev.push_back(p);
+            return Plane{p, w_, h_, p_};
+        };
+        std::vector<Plane> pin, pout;
+        for (int i = 0; i < n_in; ++i) {
+            pin.push_back(alloc(width, height, pitch));
+            DFB_CUDA(cudaMemcpy2D(pin[i].p, (size_t)pitch * 4, in[i], (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+        }
+        double *d_part = nullptr, *d_sum = nullptr;
+        auto need = [&](int ni, int no) {
+            if (n_in != ni || n_out != no) throw std::runtime_error(k + ": expects " + std::to_string(ni) + " inputs and " + std::to_string(no) + " outputs");
+        };
+        int inplace_from = -1;  // outputs that are in-place updates of inputs starting at this input index
+        if (k == "gradient") {
+            need(1, 2);
+            pout = {alloc(width, height, pitch), alloc(width, height, pitch)};
+            launch_centered_gradient(pin[0], pout[0], pout[1], nullptr);
+        } else if (k == "warp") {
+            need(6, 4);
+            for (int i = 0; i < 4; ++i) pout.push_back(alloc(width, height, pitch));
+            launch_warp_backward(pin[0], pin[1], pin[2], pin[3], pin[4], pin[5], pout[0], pout[1], pout[2], pout[3], nullptr);
+        } else if (k == "estimate_u") {
+            need(10, 2);
+            const Tvl1Consts c{(float)sc(0), 0.f, (float)sc(1)};
+            const bool calc = sc(2) != 0;
+            const int nblk = estimate_u_blocks(width, height);
+            if (calc) {
+                DFB_CUDA(cudaMalloc(&d_part, sizeof(double) * nblk));
+                DFB_CUDA(cudaMalloc(&d_sum, sizeof(double)));
+            }
+            launch_estimate_u(pin[0], pin[1], pin[2], pin[3], pin[4], pin[5], pin[6], pin[7], pin[8], pin[9], c, d_part, nullptr);
+            if (calc) {
+                launch_sum_partials(d_part, nblk, d_sum, nullptr);
+                if (scalars_out) DFB_CUDA(cudaMemcpy(scalars_out, d_sum, sizeof(double), cudaMemcpyDeviceToHost));
+            }
+            inplace_from = 8;
+        } else if (k == "estimate_dual") {
+            need(6, 4);
+            const Tvl1Consts c{0.f, (float)sc(0), 0.f};
+            launch_estimate_dual(pin[0], pin[1], pin[2], pin[3], pin[4], pin[5], c, nullptr);
+            inplace_from = 2;
+        } else if (k == "resize") {
+            need(1, 1);
+            pout = {alloc(ow, oh, opitch)};
+            launch_resize_linear(pin[0], pout[0], (float)sc(2), (float)sc(3), n_scalars > 4 ? (float)sc(4) : 1.0f, nullptr);
+        } else {
+            for (float *p : dev) cudaFree(p);
+            throw std::runtime_error("unknown debug kernel " + k);
+        }
+        DFB_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < n_out; ++i) {
+            const Plane &src = inplace_from >= 0 ? pin[inplace_from + i] : pout[i];
+            DFB_CUDA(cudaMemcpy2D(out[i], (size_t)src.w * 4, src.p, (size_t)src.pitch * 4, (size_t)src.w * 4, src.h, cudaMemcpyDeviceToHost));
+        }
+        for (float *p : dev) cudaFree(p);
+        if (d_part) cudaFree(d_part);
+        if (d_sum) cudaFree(d_sum);
+        return DFB_OK;
+    });
+}
+
 int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out) {
     if (!h || !out) return DFB_ERR_INVALID_ARG;
     return guarded(h, [&]() {

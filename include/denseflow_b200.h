@@ -145,6 +145,19 @@ typedef struct {
 } dfb_tvl1_stats;
 int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out);
 
+/*
+ * Test hook: run ONE stand-alone TV-L1 kernel on dense host planes (w*h floats each, uploaded into the engine's pitched
+ * layout, downloaded after the launch) so each kernel can be checked against the oracle's building block:
+ *   "gradient"      in {I}                                   out {Ix, Iy}
+ *   "warp"          in {I0, I1, I1x, I1y, u1, u2}            out {I1wx, I1wy, grad, rho_c}
+ *   "estimate_u"    in {I1wx,I1wy,grad,rho_c,p11,p12,p21,p22,u1,u2}  out {u1, u2}; scalars {l_t, theta, calc_error}; scalars_out[0] = sum(diff)
+ *   "estimate_dual" in {u1,u2,p11,p12,p21,p22}               out {p11,p12,p21,p22}; scalars {taut}
+ *   "resize"        in {src (w x h)}                         out {dst (scalars[0] x scalars[1])}; scalars {dw, dh, fx, fy, post_mul}
+ * Not part of the reference's surface.
+ */
+int dfb_debug_run_kernel(dfb_handle *h, const char *kernel, const float *const *in, int n_in, float *const *out, int n_out,
+                         int width, int height, const double *scalars, int n_scalars, double *scalars_out);
+
 typedef struct {
     uint64_t pairs;          /* flow fields computed */
     uint64_t kernel_launches; /* CUDA kernels launched by this handle */
