@@ -156,6 +156,26 @@ class DenseOpticalFlow:
                                                         cap, C.byref(n), C.c_void_p(s)))
         return buf[:n.value].tobytes()
 
+    # -- gray -> resize -> flow -> quantise -> JPEG for decoded BGR frames (the reference's chain minus decode / file IO) --
+    def process_bgr_batch(self, frames_bgr, step=1, bound=20, new_size=None, quality=95):
+        """frames_bgr: list of uint8 [H,W,3]; new_size: (w, h) or None.  Returns [(jpg_x bytes, jpg_y bytes)] per pair."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames_bgr]
+        n = len(frames)
+        sh, sw = frames[0].shape[:2]
+        dw, dh = new_size if new_size else (0, 0)
+        ow, oh = (dw, dh) if new_size else (sw, sh)
+        m = max(n - abs(step), 0)
+        cap = self._L.dfb_jpeg_max_bytes(ow, oh)
+        bx = [np.empty(cap, np.uint8) for _ in range(m)]
+        by = [np.empty(cap, np.uint8) for _ in range(m)]
+        fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        xp = (C.c_void_p * max(m, 1))(*[b.ctypes.data for b in bx])
+        yp = (C.c_void_p * max(m, 1))(*[b.ctypes.data for b in by])
+        lx = (C.c_size_t * max(m, 1))()
+        ly = (C.c_size_t * max(m, 1))()
+        self._check(self._L.dfb_process_bgr_batch_host(self._h, fp, n, step, sw, sh, dw, dh, int(bound), int(quality), xp, yp, cap, lx, ly))
+        return [(bx[i][:lx[i]].tobytes(), by[i][:ly[i]].tobytes()) for i in range(m)]
+
     # -- test hook: one stand-alone kernel on host planes --
     def debug_run_kernel(self, kernel, inputs, n_out, scalars=(), out_shape=None):
         inputs = [np.ascontiguousarray(a, np.float32) for a in inputs]

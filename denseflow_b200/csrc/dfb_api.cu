@@ -3,6 +3,7 @@
 // (/root/reference/src/denseflow_gpu.cpp:313-342): upload x2 (:317-318), calc (:327/:329),
 // download (:339) — plus the batch shape of the whole function (:307-342).
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -38,6 +39,10 @@ struct dfb_handle {
     uint8_t *h_q[kFlowRing] = {};
     // resize coefficient tables on the device, rebuilt when the geometry changes
     std::unique_ptr<JpegEncoder> jpeg;  // created on first use
+    // scratch of dfb_process_bgr_batch_host (grown on demand)
+    uint8_t *pb_bgr = nullptr, *pb_gray = nullptr, *pb_frames = nullptr, *pb_q = nullptr;
+    float *pb_flows = nullptr;
+    size_t pb_bgr_cap = 0, pb_gray_cap = 0, pb_frames_cap = 0, pb_q_cap = 0, pb_flows_cap = 0;
     ResizeTap *d_taps = nullptr;
     int taps_cap = 0, taps_sw = 0, taps_sh = 0, taps_dw = 0, taps_dh = 0;
 };
@@ -304,6 +309,8 @@ void dfb_destroy(dfb_handle *h) {
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
     h->jpeg.reset();
+    for (void *p : {(void *)h->pb_bgr, (void *)h->pb_gray, (void *)h->pb_frames, (void *)h->pb_q, (void *)h->pb_flows})
+        if (p) cudaFree(p);
     if (h->d_taps) cudaFree(h->d_taps);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
@@ -498,6 +505,71 @@ int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_
         DFB_CUDA(cudaSetDevice(h->device));
         if (!h->jpeg) h->jpeg.reset(new JpegEncoder());
         *out_len = h->jpeg->encode_gray(gray, gray_pitch, width, height, quality, out, out_capacity, static_cast<cudaStream_t>(stream));
+        return DFB_OK;
+    });
+}
+
+int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_frames, int step, int sw, int sh, int dw, int dh,
+                               int bound, int jpeg_quality, uint8_t *const *jpg_x, uint8_t *const *jpg_y, size_t capacity,
+                               size_t *len_x, size_t *len_y) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!bgr || n_frames < 0) return fail(h, DFB_ERR_INVALID_ARG, "frames is null");
+    if (step == 0) return fail(h, DFB_ERR_INVALID_ARG, "step must be non-zero for flow extraction");
+    if (bound <= 0) return fail(h, DFB_ERR_INVALID_ARG, "bound should > 0!");
+    if (sw <= 0 || sh <= 0 || dw < 0 || dh < 0 || (dw == 0) != (dh == 0)) return fail(h, DFB_ERR_INVALID_ARG, "bad geometry");
+    if (dw == 0) {
+        dw = sw;
+        dh = sh;
+    }
+    if (int rc = check_size(h, dw, dh)) return rc;
+    const int astep = std::abs(step);
+    const int M = std::max(n_frames - astep, 0);
+    if (M == 0) return DFB_OK;
+    if (!jpg_x || !jpg_y || !len_x || !len_y) return fail(h, DFB_ERR_INVALID_ARG, "null output");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        ensure_host_path(h);
+        cudaStream_t s = h->s_compute;
+        auto grow = [&](auto *&ptr, size_t &cap, size_t need) {
+            if (need <= cap) return;
+            DFB_CUDA(cudaStreamSynchronize(s));
+            if (ptr) DFB_CUDA(cudaFree(ptr));
+            void *p = nullptr;
+            DFB_CUDA(cudaMalloc(&p, need));
+            ptr = static_cast<std::remove_reference_t<decltype(ptr)>>(p);
+            cap = need;
+        };
+        const size_t fpx = (size_t)dw * dh;
+        grow(h->pb_bgr, h->pb_bgr_cap, (size_t)sw * sh * 3);
+        grow(h->pb_gray, h->pb_gray_cap, (size_t)sw * sh);
+        grow(h->pb_frames, h->pb_frames_cap, fpx * n_frames);
+        grow(h->pb_flows, h->pb_flows_cap, fpx * 2 * sizeof(float) * M);
+        grow(h->pb_q, h->pb_q_cap, fpx * 2);
+        // decode stage tail: BGR -> gray -> resize (src/denseflow_gpu.cpp:163-170)
+        for (int f = 0; f < n_frames; ++f) {
+            DFB_CUDA(cudaMemcpyAsync(h->pb_bgr, bgr[f], (size_t)sw * sh * 3, cudaMemcpyHostToDevice, s));
+            h->counters.h2d_bytes += (size_t)sw * sh * 3;
+            uint8_t *dst = h->pb_frames + fpx * f;
+            if (dw == sw && dh == sh) {
+                launch_bgr_to_gray(h->pb_bgr, (size_t)sw * 3, sw, sh, dst, dw, s);
+            } else {
+                launch_bgr_to_gray(h->pb_bgr, (size_t)sw * 3, sw, sh, h->pb_gray, sw, s);
+                const int rc = dfb_resize_gray_device(h, h->pb_gray, sw, sw, sh, dst, dw, dw, dh, s);
+                if (rc != DFB_OK) throw std::runtime_error(h->last_error);
+            }
+            // the staging BGR buffer is reused by the next frame: the H2D of frame f+1 is stream-ordered after this kernel
+        }
+        // flow stage (src/denseflow_gpu.cpp:313-342)
+        const int rc = dfb_calc_batch_device(h, h->pb_frames, n_frames, step, dw, dh, h->pb_flows, s);
+        if (rc != DFB_OK) throw std::runtime_error(h->last_error);
+        // encode stage (src/common.cpp:48-64): bound + quantise, then one JPEG per plane
+        if (!h->jpeg) h->jpeg.reset(new JpegEncoder());
+        for (int j = 0; j < M; ++j) {
+            launch_quantise(h->pb_flows + fpx * 2 * j, (size_t)dw * 8, dw, dh, bound, h->pb_q, h->pb_q + fpx, dw, s);
+            len_x[j] = h->jpeg->encode_gray(h->pb_q, dw, dw, dh, jpeg_quality, jpg_x[j], capacity, s);
+            len_y[j] = h->jpeg->encode_gray(h->pb_q + fpx, dw, dw, dh, jpeg_quality, jpg_y[j], capacity, s);
+            h->counters.d2h_bytes += len_x[j] + len_y[j];
+        }
         return DFB_OK;
     });
 }

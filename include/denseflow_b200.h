@@ -146,6 +146,19 @@ typedef struct {
 int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out);
 
 /*
+ * The reference's per-batch chain minus decode and file IO, on the GPU, for decoded BGR frames:
+ *   cvtColor(BGR2GRAY) src/denseflow_gpu.cpp:163 -> resize :166-170 -> flow :313-342 ->
+ *   convertFlowToImage + imencode(".jpg") x2  src/common.cpp:48-64 (what writeFlowImages then writes, :84-100).
+ * bgr[n_frames]: host pointers to packed 8-bit BGR frames (src_width x src_height, dense rows).  dst_width/dst_height:
+ * the size get_new_size chose (src/denseflow_gpu.cpp:44-80), or 0/0 for no resize.  For each of the
+ * M = max(n_frames - |step|, 0) pairs the two JPEG bitstreams are written to jpg_x[i] / jpg_y[i] (host buffers of
+ * `capacity` bytes each, dfb_jpeg_max_bytes(dst) is enough) and their lengths to len_x[i] / len_y[i].
+ */
+int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_frames, int step, int src_width, int src_height,
+                               int dst_width, int dst_height, int bound, int jpeg_quality, uint8_t *const *jpg_x,
+                               uint8_t *const *jpg_y, size_t capacity, size_t *len_x, size_t *len_y);
+
+/*
  * Test hook: run ONE stand-alone TV-L1 kernel on dense host planes (w*h floats each, uploaded into the engine's pitched
  * layout, downloaded after the launch) so each kernel can be checked against the oracle's building block:
  *   "gradient"      in {I}                                   out {Ix, Iy}
