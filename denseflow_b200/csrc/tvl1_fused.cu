@@ -26,6 +26,8 @@
 
 #include <cuda.h>
 
+#include <mutex>
+
 #include "tvl1_fused.cuh"
 #include "tvl1_math.cuh"
 
@@ -648,10 +650,16 @@ int fused_num_sms(int device) {
 }
 
 int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        configured = true;
+    // the opt-in shared-memory size is a per-device function attribute: handles on several devices may live in one process
+    static std::mutex mtx;
+    static bool configured[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        const int d = device >= 0 && device < 64 ? device : 0;
+        if (!configured[d]) {
+            DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            configured[d] = true;
+        }
     }
     static_assert(TW == kFusedTileW && TH == kFusedTileH, "tile geometry is shared with the host heuristics");
     // all CTAs must be co-resident (1 CTA / SM): group * njobs <= SM count, enforced by the cooperative launch
