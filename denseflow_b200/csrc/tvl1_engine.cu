@@ -34,6 +34,7 @@ struct Tvl1Params {
     int flag_sync = 1;
     int time_kernels = 0;
     int use_tma = 1;
+    int cluster = 1;  // 2: thread-block clusters of two CTAs share a 128 x 128 region (needs flag_sync and use_tma)
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
@@ -79,6 +80,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "flag_sync") prm_.flag_sync = (int)v;  // 0 CTA barriers, 1 spin on neighbour flags, n > 1: spin with n ns back-off
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "use_tma") prm_.use_tma = v != 0;
+        else if (k == "cluster") { if (v != 1 && v != 2) return false; prm_.cluster = (int)v; }
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -97,6 +99,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "flag_sync") *v = prm_.flag_sync;
         else if (k == "time_kernels") *v = prm_.time_kernels;
         else if (k == "use_tma") *v = prm_.use_tma;
+        else if (k == "cluster") *v = prm_.cluster;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -161,7 +164,8 @@ class Tvl1 final : public FlowAlgorithm {
             double num = 0, den = 0;
             for (int l = 0; l < n; ++l) {
                 const double wgt = l == n - 1 ? 7.0 : (l == n - 2 ? 1.5 : 1.0);
-                const int tiles = fused_tiles_along(lv[l].w, kFusedTileW, hx) * fused_tiles_along(lv[l].h, kFusedTileH, hy);
+                const int cs = effective_cluster();
+                const int tiles = cs * fused_tiles_along(lv[l].w, kFusedTileW, hx) * fused_tiles_along(lv[l].h, kFusedTileH * cs, hy);
                 const int rounds = (tiles + G - 1) / G;
                 num += wgt * tiles;
                 den += wgt * (double)rounds * G;
@@ -174,6 +178,8 @@ class Tvl1 final : public FlowAlgorithm {
         }
         return best;
     }
+
+    int effective_cluster() const { return (prm_.cluster == 2 && prm_.flag_sync && prm_.use_tma) ? 2 : 1; }
 
     void solve_batch(const PairJob *jobs, int count, int w, int h, cudaStream_t s) override {
         LevelGeom lv[kMaxScales];
@@ -430,7 +436,10 @@ class Tvl1 final : public FlowAlgorithm {
         // one CTA per SM at most: the tile counts of the largest level bound the useful group size
         const int hx = 4, hy = 1;
         const int max_tiles = fused_tiles_along(lv[0].w, kFusedTileW, hx) * fused_tiles_along(lv[0].h, kFusedTileH, hy);
-        batch.group = std::max(1, std::min(batch.group, max_tiles));
+        const int cs = effective_cluster();
+        batch.cluster = cs;
+        batch.group = std::max(1, std::min(batch.group, cs == 1 ? max_tiles : max_tiles + (max_tiles & 1)));
+        if (cs > 1) batch.group = std::max(cs, batch.group & ~1);  // whole clusters only
         if (prm_.time_kernels) {
             if (timing_used_ == kTimingRing) drain_timing();
             if (!timing_ev_[0][0])

@@ -24,6 +24,7 @@
 // branch of the A.4 state machine and results are run-to-run deterministic.
 #include <cfloat>
 
+#include <cooperative_groups.h>
 #include <cuda.h>
 
 #include <mutex>
@@ -239,6 +240,21 @@ __device__ __forceinline__ void wait_ge(const volatile int *flag, int v, unsigne
         if (backoff_ns) __nanosleep(backoff_ns);  // a spinning warp competes for issue slots with the warps it waits for
     }
 }
+// cluster-scope variants for the two warps on the seam of a 2-CTA cluster tile: the flag lives in the owning CTA's
+// shared memory and is read by the other CTA through DSMEM
+__device__ __forceinline__ void wait_ge_cluster(const int *remote_flag, int v) {
+    if ((threadIdx.x & 31) == 0) {  // one lane polls through DSMEM (~200 cycles per probe); the warp re-converges below
+        int x;
+        do {
+            asm volatile("ld.acquire.cluster.b32 %0, [%1];" : "=r"(x) : "l"(remote_flag) : "memory");
+        } while (x - v < 0);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void signal_cluster(int *flag, int v) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("st.release.cluster.b32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
 __device__ __forceinline__ void signal(volatile int *flag, int v) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -249,14 +265,19 @@ __device__ __forceinline__ void signal(volatile int *flag, int v) {
 
 __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLevel &L, int level, int cur, int tx, int ty,
                                               int kk, int hx, int hy, bool check, int base, unsigned tma_parity, Smem &sm,
-                                              bool prof_on) {
+                                              bool prof_on, int crank, int csize, Smem *sm_above, Smem *sm_below) {
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     unsigned long long t0 = 0;
     if (prof_on) t0 = gtime();
     const int W = L.w, H = L.h, P = L.pitch;
-    const int rx0 = tx * (TW - 2 * hx), ry0 = ty * (TH - 2 * hy);
+    // a cluster of csize CTAs stacked vertically shares one (TH * csize)-row region; this CTA owns rows [TH*crank, TH*crank+TH)
+    const int cth = TH * csize;
+    const int cry0 = ty * (cth - 2 * hy);
+    const int rx0 = tx * (TW - 2 * hx), ry0 = cry0 + TH * crank;
     const int gx0 = rx0 + 4 * lane;
     const int gy0 = ry0 + RPT * wq;
+    const bool seam_top = crank > 0 && wq == 0;                   // the row above belongs to the CTA above
+    const bool seam_bot = crank < csize - 1 && wq == kWarps - 1;  // the row below belongs to the CTA below
     const float taut = job.c.taut;
     volatile int *prog = sm.prog;
     const bool flagsync = job.flag_sync != 0;
@@ -270,7 +291,10 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         // TMA while every thread loads its share of the four dual planes into registers.  All warps must be done
         // with the previous tile's shared memory first (the bulk copy overwrites every slot).
         fence_proxy_async();
-        __syncthreads();
+        if (csize > 1)
+            cooperative_groups::this_cluster().sync();  // the CTA above still reads this CTA's first u row in its last dual step
+        else
+            __syncthreads();
         if (threadIdx.x == 0) {
             const char *maps = static_cast<const char *>(job.tmaps) + (size_t)level * kFusedMapsPerLevel * kTensorMapBytes;
             mbar_expect_tx(&sm.tma_bar, 6u * kConstPlane * (unsigned)sizeof(float));
@@ -318,12 +342,13 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
     const int rbot = H - 1 - gy0;   // row r == rbot of this warp is the last image row
     // which of this thread's pixels are interior (written back / counted in the error)
     const bool lane_in = (tx == 0 || 4 * lane >= hx) && 4 * lane < TW - hx + (rx0 + TW >= W ? hx : 0) && gx0 < W;
-    const int ry_lo = ty == 0 ? 0 : hy, ry_hi = TH - hy + (ry0 + TH >= H ? hy : 0);
+    const int cy_lo = ty == 0 ? 0 : hy, cy_hi = cth - hy + (cry0 + cth >= H ? hy : 0);  // valid rows of the cluster region
+    const int ry_lo = max(cy_lo - TH * crank, 0), ry_hi = min(cy_hi - TH * crank, TH);
 
     // make row RPT-1 of p12/p22 visible to the warp below before the first primal step
     st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
     st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-    signal(&prog[wq], base);
+    if (seam_bot) signal_cluster(&sm.prog[wq], base); else signal(&prog[wq], base);
     if (!flagsync) __syncthreads();
     if (prof_on) {
         const unsigned long long t = gtime();
@@ -341,6 +366,10 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             if (flagsync) wait_ge(&prog[wq - 1], base + 2 * it, backoff);
             up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
             up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
+        } else if (seam_top) {  // last warp of the CTA above, through distributed shared memory
+            wait_ge_cluster(&sm_above->prog[kWarps - 1], base + 2 * it);
+            up12 = *reinterpret_cast<const float4 *>(&sm_above->p_bot[0][kWarps - 1][4 * lane]);
+            up22 = *reinterpret_cast<const float4 *>(&sm_above->p_bot[1][kWarps - 1][4 * lane]);
         }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
@@ -385,7 +414,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
             up12 = p12[r];
             up22 = p22[r];
         }
-        signal(&prog[wq], base + 2 * it + 1);
+        if (seam_top) signal_cluster(&sm.prog[wq], base + 2 * it + 1); else signal(&prog[wq], base + 2 * it + 1);
         if (!flagsync) __syncthreads();
         // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ------------------------
         float4 c1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0]);
@@ -405,6 +434,12 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
                         d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
                         d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
                     }
+                } else if (seam_bot) {  // first row of the CTA below, through distributed shared memory
+                    wait_ge_cluster(&sm_below->prog[0], base + 2 * it + 1);
+                    if (!(edge_y && rbot == RPT - 1)) {
+                        d1 = *reinterpret_cast<const float4 *>(&sm_below->u[0][4 * lane]);
+                        d2 = *reinterpret_cast<const float4 *>(&sm_below->u[1][4 * lane]);
+                    }
                 }
             }
             float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
@@ -422,7 +457,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         }
         st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
         st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-        signal(&prog[wq], base + 2 * it + 2);
+        if (seam_bot) signal_cluster(&sm.prog[wq], base + 2 * it + 2); else signal(&prog[wq], base + 2 * it + 2);
         if (!flagsync) __syncthreads();
     }
     if (prof_on) {
@@ -499,6 +534,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
     const int G = batch.group;
     const int lane_id = blockIdx.x / G, bid = blockIdx.x - lane_id * G;
     const FusedJob &job = batch.job[lane_id];
+    // optional 2-CTA clusters (launch attribute): the two CTAs of a cluster are consecutive block indices of one lane
+    const int csize = batch.cluster, crank = csize > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+    Smem *sm_above = nullptr, *sm_below = nullptr;
+    if (csize > 1) {
+        auto cl = cooperative_groups::this_cluster();
+        if (crank > 0) sm_above = cl.map_shared_rank(&sm, crank - 1);
+        if (crank < csize - 1) sm_below = cl.map_shared_rank(&sm, crank + 1);
+    }
     unsigned epoch = 0;
     unsigned *bar = job.sync;
     int cur = 0;
@@ -549,11 +592,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     const int kk = (remaining + nch - 1) / nch;
                     const bool chk = check && kk == remaining;
                     const int hx = (kk + 3) & ~3, hy = kk;
-                    const int ntx = tiles_along(L.w, TW, hx), nty = tiles_along(L.h, TH, hy);
+                    const int ntx = tiles_along(L.w, TW, hx), nty = tiles_along(L.h, TH * csize, hy);
                     const int ntiles = ntx * nty;
-                    for (int t = bid; t < ntiles; t += G) {
+                    for (int t = bid / csize; t < ntiles; t += G / csize) {
                         const int ty = t / ntx, tx = t - ty * ntx;
-                        const float e = process_tile(job, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on);
+                        const float e = process_tile(job, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on, crank, csize, sm_above, sm_below);
                         tile_base += 2 * kk + 2;
                         tma_parity ^= 1u;
                         if (chk) {
@@ -664,8 +707,26 @@ int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
     static_assert(TW == kFusedTileW && TH == kFusedTileH, "tile geometry is shared with the host heuristics");
     // all CTAs must be co-resident (1 CTA / SM): group * njobs <= SM count, enforced by the cooperative launch
     const int grid = batch.group * batch.njobs;
-    void *args[] = {const_cast<FusedBatch *>(&batch)};
-    DFB_CUDA(cudaLaunchCooperativeKernel((const void *)k_tvl1_pair, dim3(grid), dim3(kThreads), args, sizeof(Smem), s));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
+    ++na;
+    if (batch.cluster > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = batch.cluster;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair, batch));
     return 1;
 }
 

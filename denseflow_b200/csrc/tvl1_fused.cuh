@@ -52,6 +52,7 @@ constexpr int kFusedMapsPerLevel = 8;
 constexpr int kTensorMapBytes = 128;  // sizeof(CUtensorMap)
 struct FusedBatch {
     int njobs, group;
+    int cluster;  // CTAs per thread-block cluster (1, or 2: two CTAs stacked vertically share a 128 x 128 region via DSMEM)
     FusedJob job[kFusedMaxLanes];
 };
 

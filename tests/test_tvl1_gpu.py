@@ -151,5 +151,9 @@ def test_fused_schedule_is_deterministic_and_lane_invariant():
         if ref is None:
             ref = out
         assert np.array_equal(out, ref), (lanes, flag_sync, k, tma)
+    # experimental 2-CTA thread-block clusters (128 x 128 regions, seam rows through distributed shared memory)
+    for lanes in (1, 2, 0):
+        out = _engine("default", 640, 360, lanes=lanes, cluster=2).calc_batch(list(fr), step=1)
+        assert np.array_equal(out, ref), ("cluster", lanes)
     unfused = _engine("default", 640, 360, fused=0).calc_batch(list(fr[:3]), step=1)
     assert np.array_equal(unfused, ref[:2])
