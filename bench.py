@@ -302,6 +302,9 @@ def main():
                            "+ 44 B/px per warp + level-start/upsample/merge; the kernel keeps up to k=%d iterations on chip per tile, "
                            "so its real DRAM traffic (see profiles/) is far below this figure and frac may exceed 1" % k,
             "k": k,
+            # the same kernel under the k-blocked formulation (64 B/px per tile visit of up to k iterations):
+            "achieved_blocked": (64.0 * c["pixel_chunks"] + b_other) / kt / 1e9,
+            "frac_blocked": (64.0 * c["pixel_chunks"] + b_other) / kt / 1e9 / peak,
             "algorithmic_bytes_per_launch": (b_iter + b_other) / c["timed_kernel_launches"],
             "avg_launch_ms": kt / c["timed_kernel_launches"] * 1e3,
             "pairs_per_launch": npairs / c["timed_kernel_launches"],

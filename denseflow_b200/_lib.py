@@ -10,8 +10,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATHS = {
     "default": os.path.join(_HERE, "lib", "libdenseflow_b200.so"),
     "strict": os.path.join(_HERE, "lib", "libdenseflow_b200_strict.so"),
-    "t448": os.path.join(_HERE, "lib", "libdenseflow_b200_t448.so"),
-    "t384": os.path.join(_HERE, "lib", "libdenseflow_b200_t384.so"),
 }
 
 DFB_OK = 0
@@ -31,7 +29,7 @@ class Tvl1Stats(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("kernel_launches", C.c_uint64), ("pixel_iters", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("timed_kernel_launches", C.c_uint64),
-                ("timed_kernel_ns", C.c_uint64), ("timed_kernel_pairs", C.c_uint64)]
+                ("timed_kernel_ns", C.c_uint64), ("timed_kernel_pairs", C.c_uint64), ("pixel_chunks", C.c_uint64)]
 
 
 # every symbol include/denseflow_b200.h declares, with its signature

@@ -21,9 +21,6 @@ VARIANTS = {
     "default": ("libdenseflow_b200.so", []),
     # IEEE arithmetic, no FMA contraction: used by tests to separate restatement bugs from fp noise
     "strict": ("libdenseflow_b200_strict.so", ["-DDFB_STRICT_FP", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
-    # experiments (not built by default)
-    "t448": ("libdenseflow_b200_t448.so", ["-DDFB_FUSED_THREADS=448"]),
-    "t384": ("libdenseflow_b200_t384.so", ["-DDFB_FUSED_THREADS=384"]),
 }
 
 

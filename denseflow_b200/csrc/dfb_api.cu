@@ -673,6 +673,7 @@ int dfb_get_counters(dfb_handle *h, dfb_counters *out) {
         *out = h->counters;
         out->kernel_launches = h->alg->launches;
         out->pixel_iters = h->alg->pixel_iters;
+        out->pixel_chunks = h->alg->pixel_chunks;
         h->alg->kernel_timing(&out->timed_kernel_launches, &out->timed_kernel_ns, &out->timed_kernel_pairs);
         return DFB_OK;
     });

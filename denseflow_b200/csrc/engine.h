@@ -46,10 +46,11 @@ class FlowAlgorithm {
     virtual bool get_param(const std::string &name, double *v) const = 0;
     virtual void tvl1_stats(dfb_tvl1_stats *out) { *out = dfb_tvl1_stats{}; }
     virtual void phase_ns(uint64_t *out) { for (int i = 0; i < 32; ++i) out[i] = 0; }
-    virtual void reset_counters() { launches = 0; pixel_iters = 0; }
+    virtual void reset_counters() { launches = 0; pixel_iters = 0; pixel_chunks = 0; }
     virtual void kernel_timing(uint64_t *launches_, uint64_t *ns, uint64_t *pairs) { *launches_ = *ns = *pairs = 0; }
     uint64_t launches = 0;     // kernels launched
     uint64_t pixel_iters = 0;  // tvl1: sum of level pixels over executed inner iterations
+    uint64_t pixel_chunks = 0; // fused tvl1: sum of level pixels over tile visits (k iterations each)
 };
 
 std::unique_ptr<FlowAlgorithm> make_tvl1(int device, int max_w, int max_h);

@@ -207,7 +207,11 @@ class Tvl1 final : public FlowAlgorithm {
             stats_pending_ = false;
         }
         pixel_iters = unfused_px_iters_;
-        for (auto &l : lanes_) pixel_iters += l.host_ctl->px_iters_total;
+        pixel_chunks = 0;
+        for (auto &l : lanes_) {
+            pixel_iters += l.host_ctl->px_iters_total;
+            pixel_chunks += l.host_ctl->px_chunks_total;
+        }
         out->nscales = last_nscales_;
         out->warps = prm_.warps;
         for (int s = 0; s < last_nscales_; ++s) {
@@ -492,7 +496,11 @@ class Tvl1 final : public FlowAlgorithm {
         unfused_px_iters_ = 0;
         drain_timing();
         timed_launches_ = timed_ns_ = timed_pairs_ = 0;
-        for (auto &l : lanes_) l.host_ctl->px_iters_total = 0;
+        for (auto &l : lanes_) {
+            l.host_ctl->px_iters_total = 0;
+            l.host_ctl->px_chunks_total = 0;
+        }
+        pixel_chunks = 0;
     }
     uint64_t unfused_px_iters_ = 0;
 

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
     unsigned epoch = 0;
     unsigned *bar = job.sync;
     int cur = 0;
-    unsigned long long px_iters = 0;
+    unsigned long long px_iters = 0, px_chunks = 0;
     int tile_base = 1;  // progress-counter epoch of the tile loop (sm.prog starts at 0)
     unsigned tma_parity = 0;
     Prof prof;
@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     if (chk && threadIdx.x == 0) job.partials[bid] = cta_err;
                     prof.mark(2, 8 + s);
                     if (prof.on) prof.acc[16 + s] += 1;
+                    px_chunks += (unsigned long long)(L.w * L.h);
                     grid_barrier(bar, epoch, G);
                     prof.mark(3);
                     cur ^= 1;
@@ -645,7 +646,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
     prof.mark(4);
     if (prof.on)
         for (int i = 0; i < 32; ++i) job.ctl->prof[i] = prof.acc[i];
-    if (bid == 0 && threadIdx.x == 0) job.ctl->px_iters_total += px_iters;  // single writer, launches are serialised
+    if (bid == 0 && threadIdx.x == 0) {
+        job.ctl->px_iters_total += px_iters;
+        job.ctl->px_chunks_total += px_chunks;
+    }  // single writer, launches are serialised
 
     // last CTA out resets the barrier words for the next launch
     __syncthreads();

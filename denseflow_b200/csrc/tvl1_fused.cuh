@@ -20,6 +20,7 @@ struct FusedHostCtl {
     double error;         // unfused engine: convergence sum read by the host state machine
     int iters[16 * 16];   // executed inner iterations per (scale, warp) of the last pair
     unsigned long long px_iters_total;  // sum over pairs of (level pixels x executed iterations)
+    unsigned long long px_chunks_total; // sum over pairs of (level pixels x tile visits): 64 B of state/constant traffic each
     // CTA-0 view of where the last pair's time went, in ns (globaltimer): [0] level start, [1] warps,
     // [2] tile compute, [3] grid barriers, [4] upsample+merge, [8+s] tile compute at scale s, [16+s] chunks at scale s
     unsigned long long prof[32];

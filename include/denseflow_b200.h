@@ -181,6 +181,7 @@ typedef struct {
     uint64_t timed_kernel_launches;
     uint64_t timed_kernel_ns;
     uint64_t timed_kernel_pairs;
+    uint64_t pixel_chunks;   /* fused tvl1: sum over tile visits of level pixels (each visit moves 64 B/px and runs up to k iterations) */
 } dfb_counters;
 int dfb_get_counters(dfb_handle *h, dfb_counters *out);
 
