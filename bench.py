@@ -36,7 +36,7 @@ WORKLOADS = {
     "farn_720p": ("farn", 1280, 720, 2, "synthetic 1280x720 stream, -a=farn -s=1 (BASELINE.json configs[3])"),
 }
 METRIC = "tvl1 flow-pairs/sec at 1920x1080"
-NCU_DRAM_BYTES_PER_PAIR = 2.885e9  # profiles/r1_fused_ncu_summary.md, 1080p
+NCU_DRAM_BYTES_PER_PAIR = 2.504e9  # profiles/r1_fused_ncu_summary.md, 1080p (10.015 GB for a 4-pair launch)
 
 
 def parse():
@@ -294,9 +294,9 @@ def main():
             "bound": "hbm", "kernel": "k_tvl1_pair (persistent fused TV-L1 pair kernel)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/r1_fused_ncu_summary.md:
-            # 11.54 GB for a 4-pair launch), scaled to this run's pairs per launch
+            # 10.015 GB for a 4-pair launch), scaled to this run's pairs per launch
             "traffic": NCU_DRAM_BYTES_PER_PAIR * npairs / c["timed_kernel_launches"],
-            "traffic_source": "profiles/r1_fused_ncu_summary.md (2.885 GB per 1080p pair)" if args.workload == "tvl1_1080p" else None,
+            "traffic_source": "profiles/r1_fused_ncu_summary.md (2.504 GB per 1080p pair)" if args.workload == "tvl1_1080p" else None,
             "peak_source": peak_src,
             "formulation": "algorithmic bytes = 64 B per pixel-iteration (fused primal+dual, SURVEY §8d) x executed pixel-iterations "
                            "+ 44 B/px per warp + level-start/upsample/merge; the kernel keeps up to k=%d iterations on chip per tile, "

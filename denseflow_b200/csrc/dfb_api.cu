@@ -138,8 +138,9 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
     if (M == 0) return DFB_OK;
     ensure_host_path(h);
     FlowAlgorithm &alg = *h->alg;
-    const int Bpre = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), dfb_handle::kFlowRing / 2));
-    alg.ensure_slots(Bpre + astep + 1);
+    // pairs per solve_batch call; the frame slots hold one group plus the look-ahead frame
+    const int B = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), dfb_handle::kFlowRing / 2));
+    alg.ensure_slots(B + astep + 1);
     const int nslots = alg.num_slots();
     const size_t fbytes = (size_t)w * hh;
     constexpr int FR = dfb_handle::kFrameRing, OR = dfb_handle::kFlowRing;
@@ -179,15 +180,11 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
         pending_copy[ring] = -1;
     };
 
-    const int B = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), OR / 2));
-    alg.ensure_slots(B + astep + 1);
-    const int nslots2 = alg.num_slots();
-    (void)nslots;
     std::vector<FlowAlgorithm::PairJob> jobs(B);
     for (int j0 = 0; j0 < M; j0 += B) {
         const int m = std::min(B, M - j0);
         // frames of this group (+ one ahead, so its H2D overlaps the solve)
-        const int last_needed = step > 0 ? j0 + m - 1 + astep : j0 + m - 1 + astep;
+        const int last_needed = j0 + m - 1 + astep;  // pairs j0..j0+m-1 touch frames j0..j0+m-1+|step| for either sign of step
         upload_until(std::min(last_needed + 1, n_frames - 1));
         for (int i = 0; i < m; ++i) {
             const int j = j0 + i;
@@ -196,7 +193,7 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             const int ring = j % OR;
             drain(ring);
             if (j >= OR) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_out[ring], 0));  // device output slot is free
-            jobs[i] = FlowAlgorithm::PairJob{a % nslots2, b % nslots2, h->d_flow[ring], (size_t)w * 2 * sizeof(float)};
+            jobs[i] = FlowAlgorithm::PairJob{a % nslots, b % nslots, h->d_flow[ring], (size_t)w * 2 * sizeof(float)};
         }
         alg.solve_batch(jobs.data(), m, w, hh, h->s_compute);
         for (int i = 0; i < m; ++i) {
