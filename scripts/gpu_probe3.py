@@ -6,13 +6,13 @@ import denseflow_b200 as d
 from denseflow_b200 import synth
 
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
-N = 17
+N = int(sys.argv[4]) if len(sys.argv) > 4 else 17
 fr = synth.stream(H, W, N, seed=1)
 dev = torch.from_numpy(fr).cuda()
 out = torch.empty((N - 1, H, W, 2), dtype=torch.float32, device="cuda")
 ref = None
 variants = sys.argv[3].split(',') if len(sys.argv) > 3 else ['default']
-cfgs = [(v, l, k, t) for v in variants for (l, k, t) in [(1, 8, 1), (1, 8, 2), (0, 8, 1), (0, 8, 2), (4, 8, 2), (6, 8, 2), (0, 6, 2)]]
+cfgs = [(v, l, k, t) for v in variants for (l, k, t) in [(0, 8, 1), (5, 8, 1), (6, 8, 1), (7, 8, 1), (8, 8, 1), (9, 8, 1), (10, 8, 1), (12, 8, 1), (7, 7, 1)]]
 for variant, lanes, k, fs in cfgs:
     e = d.OpticalFlowDual_TVL1.create(0, W, H, variant)
     e.set("lanes", lanes); e.set("fused_k", k); e.set("cluster", fs)

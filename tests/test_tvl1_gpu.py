@@ -157,3 +157,30 @@ def test_fused_schedule_is_deterministic_and_lane_invariant():
         assert np.array_equal(out, ref), ("cluster", lanes)
     unfused = _engine("default", 640, 360, fused=0).calc_batch(list(fr[:3]), step=1)
     assert np.array_equal(unfused, ref[:2])
+
+
+def test_one_handle_many_sizes(oracle):
+    """A handle created for a maximum size serves any smaller frame (the reference re-creates the algorithm object per
+    batch; here the workspace, pyramid slots and TMA descriptors are re-targeted when the geometry changes)."""
+    e = _engine("default", 320, 240)
+    for (h, w, seed) in [(240, 320, 1), (96, 128, 2), (240, 320, 1), (57, 311, 3), (240, 33, 4)]:
+        a, b, _ = synth.pair(h, w, seed)
+        ref = oracle.tvl1_calc(a, b)
+        assert synth.aee(e.calc(a, b), ref) <= AEE_TOL, (h, w)
+    # batches of different sizes back to back, more pairs than lanes
+    fr = synth.stream(120, 160, 20, seed=5)
+    flows = e.calc_batch(list(fr), step=1)
+    assert flows.shape == (19, 120, 160, 2)
+    assert synth.aee(flows[18], oracle.tvl1_calc(fr[18], fr[19])) <= AEE_TOL
+    assert np.array_equal(flows[7], e.calc(fr[7], fr[8]))
+
+
+def test_degenerate_batches():
+    e = _engine("default", 64, 64)
+    fr = [np.zeros((64, 64), np.uint8)] * 3
+    assert e.calc_batch(fr[:1], step=1).shape[0] == 0       # one frame: no pair (M = max(N - |step|, 0))
+    assert e.calc_batch(fr, step=5).shape[0] == 0           # |step| >= N
+    z = e.calc_batch(fr, step=-1)                           # constant frames: exactly zero flow
+    assert z.shape == (2, 64, 64, 2) and not z.any()
+    with pytest.raises(RuntimeError):
+        e.calc_batch(fr, step=0)                            # step 0 is the frame-extraction mode, not a flow request
