@@ -312,6 +312,17 @@ def main():
             "kernel_share_of_step": kt / dt_dev,
         }
 
+    # ---------------- stand-alone primal / dual kernels of the unfused schedule vs the HBM roofline ------------
+    kernels = None
+    if alg == "tvl1" and rank == 0:
+        peak, peak_src = load_peaks()
+        kernels = {}
+        for name, bpp in (("estimate_u", 48), ("estimate_dual", 40)):
+            ms = eng.debug_time_kernel(name, W, H, sets=6, reps=60)
+            gbs = bpp * W * H / (ms * 1e-3) / 1e9
+            kernels["k_" + name] = {"bytes_per_px": bpp, "ms_per_launch": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+                                    "note": "CUDA events over 60 launches rotating 6 operand sets (L2-busting), %dx%d" % (W, H)}
+
     # ---------------- e2e: host buffers through the reference-facing call ---------------------------------
     for i in range(max(args.warmup, 1)):
         step_host(i)
@@ -351,6 +362,8 @@ def main():
         }
         if roof:
             line["roofline"] = roof
+        if kernels:
+            line["unfused_kernels"] = kernels
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

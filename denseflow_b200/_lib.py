@@ -63,6 +63,7 @@ SIGNATURES = {
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "dfb_debug_run_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                        C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
+    "dfb_debug_time_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "dfb_get_tvl1_stats": (C.c_int, [C.c_void_p, C.POINTER(Tvl1Stats)]),
     "dfb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "dfb_get_tvl1_phase_ns": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

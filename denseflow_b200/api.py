@@ -189,6 +189,12 @@ class DenseOpticalFlow:
         self._check(self._L.dfb_debug_run_kernel(self._h, kernel.encode(), ip, len(inputs), op, n_out, w, h, sc, len(scalars), so))
         return outs, so[0]
 
+    def debug_time_kernel(self, kernel, width, height, sets=6, reps=60):
+        """Mean ms per launch of a stand-alone inner-loop kernel on an L2-busting rotation of operand sets."""
+        ms = C.c_double()
+        self._check(self._L.dfb_debug_time_kernel(self._h, kernel.encode(), width, height, sets, reps, C.byref(ms)))
+        return ms.value
+
     # -- counters for the roofline arithmetic --
     def tvl1_stats(self):
         st = _lib.Tvl1Stats()

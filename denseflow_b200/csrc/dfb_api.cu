@@ -652,6 +652,48 @@ int dfb_debug_run_kernel(dfb_handle *h, const char *kernel, const float *const *
     });
 }
 
+int dfb_debug_time_kernel(dfb_handle *h, const char *kernel, int width, int height, int sets, int reps, double *ms_per_launch) {
+    if (!h || !kernel || !ms_per_launch) return DFB_ERR_INVALID_ARG;
+    if (width <= 0 || height <= 0 || sets < 1 || sets > 64 || reps < 1) return fail(h, DFB_ERR_INVALID_ARG, "bad arguments");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        const std::string k(kernel);
+        const bool primal = k == "estimate_u";
+        if (!primal && k != "estimate_dual") throw std::runtime_error("unknown kernel " + k);
+        const int nplanes = primal ? 10 : 6;
+        const int pitch = round_up(width, 32);
+        const size_t pe = (size_t)pitch * (height + 1);
+        float *buf = nullptr;
+        DFB_CUDA(cudaMalloc(&buf, pe * sizeof(float) * nplanes * sets));
+        auto plane = [&](int set, int i) { return Plane{buf + ((size_t)set * nplanes + i) * pe, width, height, pitch}; };
+        for (int sidx = 0; sidx < sets; ++sidx)
+            for (int i = 0; i < nplanes; ++i) launch_fill(plane(sidx, i), 0.125f * (float)(i + 1), nullptr);
+        const Tvl1Consts c{0.045f, 0.25f / 0.3f, 0.3f};
+        auto run = [&](int sidx) {
+            if (primal)
+                launch_estimate_u(plane(sidx, 0), plane(sidx, 1), plane(sidx, 2), plane(sidx, 3), plane(sidx, 4), plane(sidx, 5), plane(sidx, 6),
+                                  plane(sidx, 7), plane(sidx, 8), plane(sidx, 9), c, nullptr, nullptr);
+            else
+                launch_estimate_dual(plane(sidx, 0), plane(sidx, 1), plane(sidx, 2), plane(sidx, 3), plane(sidx, 4), plane(sidx, 5), c, nullptr);
+        };
+        for (int i = 0; i < 3; ++i) run(i % sets);
+        cudaEvent_t e0, e1;
+        DFB_CUDA(cudaEventCreate(&e0));
+        DFB_CUDA(cudaEventCreate(&e1));
+        DFB_CUDA(cudaEventRecord(e0, nullptr));
+        for (int i = 0; i < reps; ++i) run((i + 3) % sets);
+        DFB_CUDA(cudaEventRecord(e1, nullptr));
+        DFB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_per_launch = (double)ms / reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(buf);
+        return DFB_OK;
+    });
+}
+
 int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out) {
     if (!h || !out) return DFB_ERR_INVALID_ARG;
     return guarded(h, [&]() {

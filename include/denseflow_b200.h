@@ -171,6 +171,14 @@ int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_f
 int dfb_debug_run_kernel(dfb_handle *h, const char *kernel, const float *const *in, int n_in, float *const *out, int n_out,
                          int width, int height, const double *scalars, int n_scalars, double *scalars_out);
 
+/*
+ * Benchmark hook for the two stand-alone inner-loop kernels of the unfused schedule (the launches the reference makes
+ * ~7 500 times per pair): "estimate_u" (48 B/px) or "estimate_dual" (40 B/px) at width x height.  `sets` independent
+ * copies of the operand planes are rotated between launches so the working set exceeds the L2 (sets * 83 MB at 1080p);
+ * `reps` launches are timed with CUDA events after 3 warm-up launches.  *ms_per_launch receives the mean.
+ */
+int dfb_debug_time_kernel(dfb_handle *h, const char *kernel, int width, int height, int sets, int reps, double *ms_per_launch);
+
 typedef struct {
     uint64_t pairs;          /* flow fields computed */
     uint64_t kernel_launches; /* CUDA kernels launched by this handle */
