@@ -323,6 +323,24 @@ def main():
             kernels["k_" + name] = {"bytes_per_px": bpp, "ms_per_launch": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
                                     "note": "CUDA events over 60 launches rotating 6 operand sets (L2-busting), %dx%d" % (W, H)}
 
+    # ---------------- the reference's launch structure on the same GPU (one kernel per half-step, host-side checks) ----
+    unfused = None
+    if alg == "tvl1" and rank == 0:
+        eu = d.create(alg, local_rank, W, H)
+        eu.set("fused", 0)
+        nq = min(P, 4)
+        eu.calc_batch_device(frames_dev[0][:nq + 1], 1, flows_dev[:nq])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()  # host clock: this schedule synchronises with the host at every convergence check
+        eu.calc_batch_device(frames_dev[1][:nq + 1], 1, flows_dev[:nq])
+        torch.cuda.synchronize(dev)
+        dtu = time.perf_counter() - t0
+        cu = eu.counters()
+        unfused = {"value": nq / dtu, "unit": "pairs/s", "kernel_launches_per_pair": cu["kernel_launches"] / (2 * nq),
+                   "note": "same arithmetic, fused=0: ~2 000 launches and one stream sync per convergence check per pair, as "
+                           "cv::cuda::OpticalFlowDual_TVL1 is structured (OpenCV-CUDA itself is not installable here)"}
+        eu.release()
+
     # ---------------- e2e: host buffers through the reference-facing call ---------------------------------
     for i in range(max(args.warmup, 1)):
         step_host(i)
@@ -364,6 +382,8 @@ def main():
             line["roofline"] = roof
         if kernels:
             line["unfused_kernels"] = kernels
+        if unfused:
+            line["unfused_schedule"] = unfused
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
