@@ -78,6 +78,52 @@ __global__ void __launch_bounds__(256) k_gauss_blur(Plane src, Plane dst, const 
     }
 }
 
+// ---- B.2 fused for levels with scale < 1: blur + resize, evaluated only where the resize looks -----------------
+// The reference blurs the WHOLE full-resolution frame for every level and then samples it with a bilinear resize that
+// reads just two rows / two columns per level pixel.  These two kernels compute exactly those samples — the vertical
+// pass only on the 2 * H_level rows the resize touches, the horizontal pass only at the 2 x 2 taps of each level pixel —
+// with the same operation order per value (vertical first; centre tap, then symmetric pairs), so the level image is
+// bit-identical to blur-then-resize while the work drops from ~70 to ~24 taps per full-resolution pixel and level set.
+__global__ void __launch_bounds__(256) k_gauss_vert_rows(Plane src, Plane vn /* 2*Hl rows */, float rfy, const GaussKernel gk) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int ri = blockIdx.y;  // row pair index: level row ri >> 1, tap ri & 1
+    if (x >= src.w) return;
+    const float sy = (ri >> 1) * rfy;
+    const int y1 = __float2int_rd(sy);
+    const int y = (ri & 1) ? min(y1 + 1, src.h - 1) : min(y1, src.h - 1);
+    float acc = src.p[(size_t)y * src.pitch + x] * gk.k[0];
+    for (int j = 1; j <= gk.half; ++j)
+        acc = acc + (src.p[(size_t)reflect101(y - j, src.h) * src.pitch + x] + src.p[(size_t)reflect101(y + j, src.h) * src.pitch + x]) * gk.k[j];
+    vn.p[(size_t)ri * vn.pitch + x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_gauss_horz_resize(Plane vn, int src_w, int src_h, Plane dst, float rfx, float rfy, const GaussKernel gk) {
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= dst.w || dy >= dst.h) return;
+    const float sx = dx * rfx, sy = dy * rfy;
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int xc[2] = {min(x1, src_w - 1), min(x2, src_w - 1)};
+    (void)src_h;
+    float b[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float *row = vn.p + (size_t)(2 * dy + r) * vn.pitch;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float acc = row[xc[c]] * gk.k[0];
+            for (int j = 1; j <= gk.half; ++j) acc = acc + (row[reflect101(xc[c] - j, src_w)] + row[reflect101(xc[c] + j, src_w)]) * gk.k[j];
+            b[r][c] = acc;
+        }
+    }
+    float out = 0.f;  // same accumulation order as k_resize_linear
+    out = out + b[0][0] * ((x2 - sx) * (y2 - sy));
+    out = out + b[0][1] * ((sx - x1) * (y2 - sy));
+    out = out + b[1][0] * ((x2 - sx) * (sy - y1));
+    out = out + b[1][1] * ((sx - x1) * (sy - y1));
+    dst.p[(size_t)dy * dst.pitch + dx] = out;
+}
+
 // ---- B.3 polynomial expansion (polyN = 5): vertical pass (t0,t1,t2) then horizontal, index-clamped ----
 constexpr int PT = 32;
 
@@ -523,15 +569,24 @@ class Farneback final : public FlowAlgorithm {
             const Level &L = ls.lv[l];
             const GaussKernel gk = gaussian_kernel(L.smooth, L.sigma);
             if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
-            const Plane blurred{blurred_, w, h, pitch_full};
-            k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame, blurred, gk);
-            DFB_KERNEL_CHECK();
             const Plane img{img_, L.w, L.h, L.pitch};
             const float rfx = (float)(1.0 / ((double)L.w / (double)w)), rfy = (float)(1.0 / ((double)L.h / (double)h));
-            launch_resize_linear(blurred, img, rfx, rfy, 1.0f, s);
+            if (L.w == w && L.h == h) {
+                // full resolution: the resize is the identity (weights 1, 0, 0, 0), blur straight into the level image
+                k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame, img, gk);
+                DFB_KERNEL_CHECK();
+                launches += 1;
+            } else {
+                const Plane vn{blurred_, w, 2 * L.h, pitch_full};  // 2 * H_level <= h rows: fits the full-resolution scratch plane
+                k_gauss_vert_rows<<<dim3(ceil_div(w, 256), 2 * L.h), 256, 0, s>>>(frame, vn, rfy, gk);
+                DFB_KERNEL_CHECK();
+                k_gauss_horz_resize<<<dim3(ceil_div(L.w, 32), ceil_div(L.h, 8)), dim3(32, 8), 0, s>>>(vn, w, h, img, rfx, rfy, gk);
+                DFB_KERNEL_CHECK();
+                launches += 2;
+            }
             k_poly_exp<5><<<dim3(ceil_div(L.w, PT), ceil_div(L.h, PT)), 256, 0, s>>>(img, r_planes(slot, L), pc);
             DFB_KERNEL_CHECK();
-            launches += 3;
+            launches += 1;
         }
     }
 
