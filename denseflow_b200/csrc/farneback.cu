@@ -255,7 +255,11 @@ __global__ void __launch_bounds__(256) k_update_matrices(const __grid_constant__
 // second shared buffer, then horizontally; the solve and the rebuild of M for the next iteration happen in
 // registers.  Global reads of M drop from 13 vertical taps x 5 planes per column to 1.9 per output pixel and plane.
 // M is double-buffered across iterations (Mout != Min): a neighbouring tile's window must still see this iteration's M.
-constexpr int BW = 32, BH = 32;
+constexpr int BW = 32;
+#ifndef DFB_FARN_BH
+#define DFB_FARN_BH 16
+#endif
+constexpr int BH = DFB_FARN_BH;  // 16: 512-pixel tiles, 38 KB of shared memory, 5 CTAs / SM (the kernel is latency-bound)
 
 template <int HALF>
 __global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
@@ -297,38 +301,52 @@ __global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant_
         }
     }
     __syncthreads();
-    // horizontal sums + solve + rebuild: each thread owns 4 consecutive pixels of one row (16-float window per plane)
+    // horizontal sums + solve + rebuild: each thread owns PX consecutive pixels of one row
     constexpr float area_inv = 1.f / (float)((1 + 2 * HALF) * (1 + 2 * HALF));
-    static_assert(BW * BH == 256 * 4 && BW % 4 == 0 && (BW + 2 * HALF) % 4 == 0, "one pass, float4-aligned rows");
+    constexpr int PX = BW * BH / 256;
+    static_assert(PX == 1 || PX == 2 || PX == 4, "tile must be 256, 512 or 1024 pixels");
+    static_assert((2 * HALF) % PX == 0 && (BW + 2 * HALF) % PX == 0, "vector-aligned rows");
     {
-        const int ty = tid / (BW / 4), tx0 = (tid % (BW / 4)) * 4;
+        const int ty = tid / (BW / PX), tx0 = (tid % (BW / PX)) * PX;
         const int y = y0 + ty;
-        float b[4][5];
+        float b[PX][5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            float v[4 + 2 * HALF];
+            float v[PX + 2 * HALF];
+            if (PX == 4) {
 #pragma unroll
-            for (int q = 0; q < (4 + 2 * HALF) / 4; ++q) {
-                const float4 t = *reinterpret_cast<const float4 *>(&vs[k][ty][tx0 + 4 * q]);
-                v[4 * q] = t.x;
-                v[4 * q + 1] = t.y;
-                v[4 * q + 2] = t.z;
-                v[4 * q + 3] = t.w;
+                for (int q = 0; q < (PX + 2 * HALF) / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&vs[k][ty][tx0 + 4 * q]);
+                    v[4 * q] = t.x;
+                    v[4 * q + 1] = t.y;
+                    v[4 * q + 2] = t.z;
+                    v[4 * q + 3] = t.w;
+                }
+            } else if (PX == 2) {
+#pragma unroll
+                for (int q = 0; q < (PX + 2 * HALF) / 2; ++q) {
+                    const float2 t = *reinterpret_cast<const float2 *>(&vs[k][ty][tx0 + 2 * q]);
+                    v[2 * q] = t.x;
+                    v[2 * q + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PX + 2 * HALF; ++q) v[q] = vs[k][ty][tx0 + q];
             }
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
+            for (int o = 0; o < PX; ++o) {
                 float acc = v[o + HALF];
 #pragma unroll
                 for (int j = 1; j <= HALF; ++j) acc = acc + (v[o + HALF - j] + v[o + HALF + j]);
                 b[o][k] = acc * area_inv;
             }
         }
-        // all four pixels' gathers are issued before any of them is consumed: coordinates are clamped into the image
+        // all pixels' gathers are issued before any of them is consumed: coordinates are clamped into the image
         // (safe reads), only the stores are predicated
         const int yc = min(y, h - 1);
-        float nfx[4], nfy[4], m[4][5];
+        float nfx[PX], nfy[PX], m[PX][5];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
+        for (int o = 0; o < PX; ++o) {
             // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
             const float det_inv = f_rcp(b[o][0] * b[o][2] - b[o][1] * b[o][1] + 1e-3f);
             nfx[o] = (b[o][0] * b[o][4] - b[o][1] * b[o][3]) * det_inv;
@@ -336,10 +354,10 @@ __global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant_
         }
         if (rebuild) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) update_matrices_px(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], R0, R1, m[o]);
+            for (int o = 0; o < PX; ++o) update_matrices_px(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], R0, R1, m[o]);
         }
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
+        for (int o = 0; o < PX; ++o) {
             const int x = x0 + tx0 + o;
             if (x < w && y < h) {
                 const size_t oo = (size_t)y * pitch + x;
