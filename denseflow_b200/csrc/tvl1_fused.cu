@@ -41,7 +41,10 @@ namespace {
 #endif
 constexpr int kThreads = DFB_FUSED_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int RPT = 4;            // rows per thread
+#ifndef DFB_FUSED_RPT
+#define DFB_FUSED_RPT 4
+#endif
+constexpr int RPT = DFB_FUSED_RPT;  // rows per thread
 constexpr int TW = 128;           // tile width  = 32 lanes x 4 px
 constexpr int TH = kWarps * RPT;  // tile height = 64
 constexpr int kConstPlane = TW * TH;

@@ -65,7 +65,10 @@ __host__ __device__ inline int fused_tiles_along(int n, int T, int h) {
 #ifndef DFB_FUSED_THREADS
 #define DFB_FUSED_THREADS 512
 #endif
-constexpr int kFusedTileW = 128, kFusedTileH = DFB_FUSED_THREADS / 32 * 4;
+#ifndef DFB_FUSED_RPT
+#define DFB_FUSED_RPT 4
+#endif
+constexpr int kFusedTileW = 128, kFusedTileH = DFB_FUSED_THREADS / 32 * DFB_FUSED_RPT;
 
 int fused_num_sms(int device);
 // Encodes one 2-D fp32 tile descriptor (box 128 x 64, no swizzle, zero fill out of bounds) into out[128 bytes].

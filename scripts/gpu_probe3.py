@@ -12,7 +12,7 @@ dev = torch.from_numpy(fr).cuda()
 out = torch.empty((N - 1, H, W, 2), dtype=torch.float32, device="cuda")
 ref = None
 variants = sys.argv[3].split(',') if len(sys.argv) > 3 else ['default']
-cfgs = [(v, l, k, t) for v in variants for (l, k, t) in [(0, 8, 1), (5, 8, 1), (6, 8, 1), (7, 8, 1), (8, 8, 1), (9, 8, 1), (10, 8, 1), (12, 8, 1), (7, 7, 1)]]
+cfgs = [(v, l, k, t) for v in variants for (l, k, t) in [(1, 8, 1), (0, 8, 1), (4, 8, 1), (0, 6, 1)]]
 for variant, lanes, k, fs in cfgs:
     e = d.OpticalFlowDual_TVL1.create(0, W, H, variant)
     e.set("lanes", lanes); e.set("fused_k", k); e.set("cluster", fs)

@@ -61,3 +61,18 @@ def test_product_never_imports_the_oracle():
         if path.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
             src = open(path).read()
             assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/ ", ""), path
+
+
+def test_cpp_host_links_against_the_header_only(built, tmp_path):
+    """examples/c_abi_host.cpp uses nothing but include/denseflow_b200.h; error behaviour = message + exit 1
+    (tools/denseflow.cpp:93-96)."""
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_example()
+    raw = tmp_path / "f.raw"
+    raw.write_bytes(bytes(64 * 64 * 2))
+    r = subprocess.run([exe, str(raw), "64", "64", "2", "lk", "1", "20", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown optical algorithm lk" in r.stderr
+    r = subprocess.run([exe, str(raw), "64", "64", "2", "tvl1", "1", "0", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "bound should > 0!" in r.stderr
+    assert subprocess.run([exe], capture_output=True).returncode == 0  # no arguments: usage, exit 0 (tools/denseflow.cpp:26-29)
