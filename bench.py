@@ -285,11 +285,13 @@ def main():
         k = int(eng.get("fused_k"))
         # algorithmic bytes: fused primal+dual iteration 64 B/px.iter (10 plane reads + 6 writes),
         # warp 44 B/px.warp, level start 28 B/px (I1 read, I1x/I1y + 4 p planes written), upsample 2*10 B/px_dst, merge 16 B/px
-        b_iter = 64.0 * c["pixel_iters"]
+        b_iter = 64.0 * c["pixel_iters"]    # per-iteration formulation (k = 1): 64 B per pixel and iteration
+        b_visit = 64.0 * c["pixel_chunks"]  # k-blocked formulation: 64 B per pixel and tile visit (<= k iterations on chip)
         b_other = npairs * (44.0 * warps * sum_px + 28.0 * sum_px + 20.0 * (sum_px - sizes[-1][0] * sizes[-1][1]) + 16.0 * W * H)
         kt = c["timed_kernel_ns"] / 1e9
         peak, peak_src = load_peaks()
-        achieved = (b_iter + b_other) / kt / 1e9
+        achieved = (b_visit + b_other) / kt / 1e9
+        equiv = (b_iter + b_other) / kt / 1e9
         roof = {
             "bound": "hbm", "kernel": "k_tvl1_pair (persistent fused TV-L1 pair kernel)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -298,17 +300,20 @@ def main():
             "traffic": NCU_DRAM_BYTES_PER_PAIR * npairs / c["timed_kernel_launches"],
             "traffic_source": "profiles/r1_fused_ncu_summary.md (2.504 GB per 1080p pair)" if args.workload == "tvl1_1080p" else None,
             "peak_source": peak_src,
-            "formulation": "algorithmic bytes = 64 B per pixel-iteration (fused primal+dual, SURVEY §8d) x executed pixel-iterations "
-                           "+ 44 B/px per warp + level-start/upsample/merge; the kernel keeps up to k=%d iterations on chip per tile, "
-                           "so its real DRAM traffic (see profiles/) is far below this figure and frac may exceed 1" % k,
+            "formulation": "SURVEY §8d, temporally blocked fused primal+dual: algorithmic bytes = 64 B per pixel per tile visit "
+                           "(10 plane reads + 6 writes; up to k=%d iterations stay on chip per visit) x executed pixel-visits "
+                           "+ 44 B/px per warp + level-start/upsample/merge.  The kernel is bound by instruction-level parallelism, "
+                           "not by HBM (DESIGN.md §4.4), hence the low fraction; `per_iteration_equivalent` restates the same run "
+                           "under the k=1 figure (64 B per pixel and iteration), i.e. the bandwidth an unblocked fused kernel "
+                           "would need to match it" % k,
             "k": k,
-            # the same kernel under the k-blocked formulation (64 B/px per tile visit of up to k iterations):
-            "achieved_blocked": (64.0 * c["pixel_chunks"] + b_other) / kt / 1e9,
-            "frac_blocked": (64.0 * c["pixel_chunks"] + b_other) / kt / 1e9 / peak,
-            "algorithmic_bytes_per_launch": (b_iter + b_other) / c["timed_kernel_launches"],
+            "algorithmic_bytes_per_launch": (b_visit + b_other) / c["timed_kernel_launches"],
+            "per_iteration_equivalent": {"achieved": equiv, "frac": equiv / peak,
+                                         "algorithmic_bytes_per_launch": (b_iter + b_other) / c["timed_kernel_launches"]},
             "avg_launch_ms": kt / c["timed_kernel_launches"] * 1e3,
             "pairs_per_launch": npairs / c["timed_kernel_launches"],
             "pixel_iters_per_pair": c["pixel_iters"] / max(npairs, 1),
+            "pixel_visits_per_pair": c["pixel_chunks"] / max(npairs, 1),
             "kernel_share_of_step": kt / dt_dev,
         }
 
