@@ -7,18 +7,24 @@
 // merge — with the A.4 convergence state machine evaluated on the device.  The reference needs
 // ~2 000 launches and a host sync per convergence check for the same work.
 //
-// Inner loop (the hot part).  The image is cut into 128 x 64 register tiles.  A CTA of 16 warps
-// owns one tile at a time: lane l of warp q holds pixels x = 4l..4l+3 of rows 4q..4q+3 — the six
-// state planes (u1,u2,p11,p12,p21,p22) live in registers, the four per-warp constants
-// (I1wx,I1wy,grad,rho_c) in shared memory.  Horizontal neighbours come from warp shuffles,
-// vertical neighbours from the thread's own next/previous row or, across warps, from a one-row
-// shared-memory exchange.  k primal+dual iterations run on chip per tile visit (halo = k, the
-// valid region shrinks by one pixel per half-step pair, exactly preserving the reference's Jacobi
-// ordering: dual sees the fully updated u, the next primal the fully updated p), then the
-// interior is written to the other half of a ping-pong pair.  Compulsory HBM traffic is
-// 64 B/px per k iterations instead of 88 B/px per iteration.
+// Inner loop (the hot part).  The image is cut into 128 x 64 tiles.  A CTA of 16 warps owns one tile
+// at a time: lane l of warp q owns pixels x = 4l..4l+3 of rows 4q..4q+3.  The four dual planes
+// (p11,p12,p21,p22) live in registers; u1,u2 and the four per-warp constants (I1wx,I1wy,grad,rho_c)
+// live in shared memory (192 KB), staged there by TMA (cp.async.bulk.tensor.2d + mbarrier, zero
+// fill outside the image) while the threads load the dual planes.  Horizontal neighbours come
+// from warp shuffles, vertical neighbours from the thread's own rows, the shared u tile, or a
+// one-row shared-memory exchange of p12/p22 between adjacent warps.  k primal+dual iterations run
+// on chip per tile visit (halo = k, the valid region shrinks by one pixel per iteration, exactly
+// preserving the reference's Jacobi ordering: dual sees the fully updated u, the next primal the
+// fully updated p), then the interior is written to the other half of a ping-pong pair.
+// Compulsory HBM traffic is 64 B/px per k iterations instead of 88 B/px per iteration.
 //
-// Grid-wide ordering uses a monotonically counting barrier in global memory (all CTAs are
+// Several independent pairs ("lanes") share one launch: lane i runs on CTAs [i*G, (i+1)*G) with its
+// own workspace, barrier words and TMA descriptors, so the coarse scales (fewer tiles than SMs)
+// do not leave SMs idle.  Optionally (cluster = 2) two CTAs of a thread-block cluster stack
+// vertically into a 128 x 128 region and exchange their seam rows through distributed shared memory.
+//
+// Grid-wide ordering uses a monotonically counting barrier in global memory per lane (all CTAs are
 // co-resident: cooperative launch).  The convergence error is reduced in a fixed order
 // (per-CTA partial -> every CTA sums all partials identically), so every CTA takes the same
 // branch of the A.4 state machine and results are run-to-run deterministic.
