@@ -359,6 +359,23 @@ def main():
     shard.barrier()
     dt_host_max = shard.all_max(dt_host, dev)
     e2e_value = total_pairs / dt_host_max
+    # same end-to-end call, but the flow is bounded + quantised on the GPU and the two uint8 planes come back
+    # (dfb_calc_batch_host_u8, SURVEY §8 f1: what the jpg path needs; 2 B/px instead of 8 B/px over PCIe)
+    qx_pin = torch.empty((P, H, W), dtype=torch.uint8).pin_memory()
+    qy_pin = torch.empty((P, H, W), dtype=torch.uint8).pin_memory()
+    qx_np, qy_np = qx_pin.numpy(), qy_pin.numpy()
+
+    def step_host_u8(i):
+        eng.calc_batch_u8_into(fr_lists[i % NWIN], 1, 20, qx_np, qy_np)
+
+    step_host_u8(0)
+    torch.cuda.synchronize(dev)
+    shard.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host_u8(args.warmup + i)
+    torch.cuda.synchronize(dev)
+    dt_u8_max = shard.all_max(time.perf_counter() - t0, dev)
     clocks = sampler.stop(tmark0, tmark1) if rank == 0 else None
 
     # ---------------- cpu baseline: bounded sample of the same workload on the host cores -----------------
@@ -380,6 +397,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": n_frames * W * H,
                     "d2h_bytes_per_step": P * W * H * 8, "ms_per_step": dt_host_max / args.steps * 1e3,
                     "call": "dfb_calc_batch_host (pinned host frames in, pinned host CV_32FC2 flows out)"},
+            "e2e_quantised": {"value": total_pairs / dt_u8_max, "unit": "pairs/s", "h2d_bytes_per_step": n_frames * W * H,
+                              "d2h_bytes_per_step": P * W * H * 2,
+                              "call": "dfb_calc_batch_host_u8 (bound 20: the two uint8 planes convertFlowToImage would produce)"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

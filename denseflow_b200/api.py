@@ -104,6 +104,18 @@ class DenseOpticalFlow:
         self._check(self._L.dfb_calc_batch_host_u8(self._h, fp, n, step, w, h, int(bound), xp, yp))
         return qx, qy
 
+    def calc_batch_u8_into(self, frames, step, bound, qx, qy):
+        """calc_batch(..., bound=B) writing into caller-provided (e.g. pinned) uint8 arrays qx, qy of shape [M,H,W]."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        n = len(frames)
+        h, w = frames[0].shape
+        m = max(n - abs(step), 0)
+        fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        xp = (C.c_void_p * max(m, 1))(*[qx[i].ctypes.data for i in range(m)])
+        yp = (C.c_void_p * max(m, 1))(*[qy[i].ctypes.data for i in range(m)])
+        self._check(self._L.dfb_calc_batch_host_u8(self._h, fp, n, step, w, h, int(bound), xp, yp))
+        return qx, qy
+
     def calc_batch_device(self, frames, step=1, flows=None, stream=None):
         """frames: CUDA uint8 tensor [N,H,W] (contiguous); flows: CUDA float32 [M,H,W,2]."""
         import torch
