@@ -60,7 +60,11 @@ const char *dfb_last_error(const dfb_handle *h);
  * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations"
  * "scale_step"; engine knobs: "fused" (1 = persistent fused primal+dual kernel [default], 0 = one
  * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile),
- * "lanes" (pairs solved side by side per launch, 0 = auto), "flag_sync", "time_kernels".
+ * "lanes" (pairs solved side by side per launch, 0 = auto, up to 16), "flag_sync" (1 = neighbour-warp progress flags
+ * in the tile loop [default], 0 = CTA-wide barriers), "use_tma" (1 = TMA staging of the shared-memory tiles [default]),
+ * "cluster" (2 = experimental 2-CTA thread-block clusters, default 1), "time_kernels" (CUDA-event timing of the fused
+ * kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma" (winSize 13, polyN 5, pyrScale 0.5 are fixed).
+ * Every combination of the engine knobs produces bit-identical flows.
  */
 int dfb_set_param(dfb_handle *h, const char *name, double value);
 int dfb_get_param(const dfb_handle *h, const char *name, double *value);
