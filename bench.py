@@ -36,7 +36,25 @@ WORKLOADS = {
     "farn_720p": ("farn", 1280, 720, 2, "synthetic 1280x720 stream, -a=farn -s=1 (BASELINE.json configs[3])"),
 }
 METRIC = "tvl1 flow-pairs/sec at 1920x1080"
-NCU_DRAM_BYTES_PER_PAIR = 2.504e9  # profiles/r1_fused_ncu_summary.md, 1080p (10.015 GB for a 4-pair launch)
+NWIN = 2  # distinct input windows of pairs+1 frames each, alternated between steps (both arms)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# captures (scripts/ncu_traffic.py writes this file from the raw CSV pages under profiles/)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+
+def ncu_traffic(workload, pairs_per_launch):
+    """Measured DRAM bytes per launch for this workload at the capture whose pairs-per-launch is closest to the
+    run's, scaled by the pair ratio; (None, reason) when no capture is committed."""
+    try:
+        caps = json.load(open(NCU_TRAFFIC_FILE)).get(workload, [])
+    except Exception:
+        caps = []
+    if not caps:
+        return None, "no ncu capture committed for this workload"
+    best = min(caps, key=lambda c_: abs(c_["pairs_per_launch"] - pairs_per_launch))
+    scale = pairs_per_launch / best["pairs_per_launch"]
+    return best["dram_bytes_per_launch"] * scale, "%s (%d-pair launch, %.3f GB DRAM read+write; scaled x%.2f to this run's pairs per launch)" % (
+        best["source"], best["pairs_per_launch"], best["dram_bytes_per_launch"] / 1e9, scale)
 
 
 def parse():
@@ -152,12 +170,16 @@ def cpu_port_throughput(alg, frames, n_pairs_per_proc, warm=True):
     n = len(frames) - 1
     jobs = [(alg, frames[i % n], frames[i % n + 1], threads) for i in range(procs * n_pairs_per_proc)]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
+    pool = ctx.Pool(procs)
+    try:
         if warm:
             pool.map(_cpu_worker, jobs[:procs])
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
     return {"value": len(jobs) / dt, "unit": "pairs/s", "cores": procs * threads, "kind": "port",
             "sample": "%d pairs of the same stream (%d processes x %d OpenMP threads, %d pairs each, after one warm-up pair per process); "
                       "CPU restatement of the CUDA algorithm (oracle/): OpenCV CPU DualTVL1 (contrib) is not installed and the reference "
@@ -165,38 +187,53 @@ def cpu_port_throughput(alg, frames, n_pairs_per_proc, warm=True):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def bench_config(args, alg, W, H, desc):
+    """The `config` object both arms print (same workload, same frames, same pairs per step)."""
+    P = args.pairs
+    return {"workload": desc, "algorithm": alg, "width": W, "height": H, "step": 1, "pairs_per_step": P,
+            "frames_per_step": P + 1, "sharding": "one independent frame stream per rank, no collective",
+            "l2": "no explicit flush: per-pair working set (16 fp32 planes x 5 levels, ~0.3 GB x lanes) exceeds the 126 MB L2 "
+                  "and consecutive steps alternate between two input windows",
+            "aee_tolerance_px": 0.01}
+
+
 def run_reference(args, alg, W, H, seed, desc):
-    """--impl reference: the reference path's CPU implementation (oracle port) on the host cores; rank 0 only."""
+    """--impl reference: the reference path's CPU implementation (oracle port) on the host cores; rank 0 only.
+    Same frames and the same pairs per step as the GPU arm: step i solves the P pairs of input window i % NWIN."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    frames = make_stream(W, H, 9, seed, 0)
+    P = args.pairs
+    frames = make_stream(W, H, NWIN * (P + 1), seed, 0).reshape(NWIN, P + 1, H, W)
     cores_all = usable_cores()
     threads = min(8, cores_all)
     procs = max(1, cores_all // threads)
     cores = procs * threads
-    n = len(frames) - 1
-    step_jobs = [(alg, frames[i % n], frames[i % n + 1], threads) for i in range(procs)]  # one step = one pair per process
+    step_jobs = [[(alg, frames[w][i], frames[w][i + 1], threads) for i in range(P)] for w in range(NWIN)]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        for _ in range(args.warmup):
-            pool.map(_cpu_worker, step_jobs, chunksize=1)
+    pool = ctx.Pool(procs)
+    try:
+        for i in range(args.warmup):
+            pool.map(_cpu_worker, step_jobs[i % NWIN], chunksize=1)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_cpu_worker, step_jobs, chunksize=1)
+        for i in range(args.steps):
+            pool.map(_cpu_worker, step_jobs[(args.warmup + i) % NWIN], chunksize=1)
         dt = time.perf_counter() - t0
-    value = args.steps * procs / dt
-    sample = ("each step = %d pairs of the workload stream solved concurrently (%d processes x %d OpenMP threads = all %d host cores); "
-              "bounded sample" % (procs, procs, threads, cores))
+    finally:
+        pool.close()  # let the workers exit on their own (a terminate() would lose their atexit records)
+        pool.join()
+    value = args.steps * P / dt
+    sample = ("each step = the %d pairs of one input window of the workload stream (the GPU arm's frames), spread over %d processes x %d "
+              "OpenMP threads = all %d usable host cores" % (P, procs, threads, cores))
     line = {
-        "impl": "reference", "metric": METRIC if args.workload == "tvl1_1080p" else "%s flow-pairs/sec" % alg,
+        "impl": "reference", "metric": METRIC if args.workload == "tvl1_1080p" else "%s flow-pairs/sec at %dx%d" % (alg, W, H),
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "algorithm": alg, "width": W, "height": H, "pairs_per_step": procs,
-                   "note": "CPU restatement of the reference's CUDA algorithm (oracle port); the reference itself needs "
-                           "OpenCV-CUDA+Boost and cannot be built in this image; OpenCV CPU DualTVL1 (contrib) is not installed"},
+        "config": bench_config(args, alg, W, H, desc),
+        "note": "CPU restatement of the reference's CUDA algorithm (oracle port, -O2 scalar C + OpenMP: a soft baseline); the reference "
+                "itself needs OpenCV-CUDA+Boost and cannot be built in this image; OpenCV CPU DualTVL1 (contrib) is not installed",
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,7 +265,6 @@ def main():
 
     P = args.pairs
     n_frames = P + 1
-    NWIN = 2  # distinct input windows, alternated between steps
     frames_np = make_stream(W, H, NWIN * n_frames, seed, rank).reshape(NWIN, n_frames, H, W)
     frames_pin = [torch.from_numpy(frames_np[w]).pin_memory() for w in range(NWIN)]
     frames_dev = [f.to(dev) for f in frames_pin]
@@ -295,10 +331,9 @@ def main():
         roof = {
             "bound": "hbm", "kernel": "k_tvl1_pair (persistent fused TV-L1 pair kernel)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/r1_fused_ncu_summary.md:
-            # 10.015 GB for a 4-pair launch), scaled to this run's pairs per launch
-            "traffic": NCU_DRAM_BYTES_PER_PAIR * npairs / c["timed_kernel_launches"],
-            "traffic_source": "profiles/r1_fused_ncu_summary.md (2.504 GB per 1080p pair)" if args.workload == "tvl1_1080p" else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+            "traffic": ncu_traffic(args.workload, npairs / c["timed_kernel_launches"])[0],
+            "traffic_source": ncu_traffic(args.workload, npairs / c["timed_kernel_launches"])[1],
             "peak_source": peak_src,
             "formulation": "SURVEY §8d, temporally blocked fused primal+dual: algorithmic bytes = 64 B per pixel per tile visit "
                            "(10 plane reads + 6 writes; up to k=%d iterations stay on chip per visit) x executed pixel-visits "
@@ -378,6 +413,27 @@ def main():
     dt_u8_max = shard.all_max(time.perf_counter() - t0, dev)
     clocks = sampler.stop(tmark0, tmark1) if rank == 0 else None
 
+    # ---------------- parity of this run's output (outside the timed region): one flow of the timed workload vs the oracle ----
+    parity = None
+    if rank == 0:
+        from oracle import pyoracle as O
+        from denseflow_b200 import synth
+        O.lib().orc_set_num_threads(min(16, usable_cores()))
+        step_device(0)  # window 0 again: flows_dev[j] = flow(frame j -> j+1)
+        torch.cuda.synchronize(dev)
+        j = P - 1  # the last pair of the step (at 1080p it is in the partial launch)
+        got = flows_dev[j].cpu().numpy()
+        if alg == "tvl1":
+            ref, ref_log = O.tvl1_calc(frames_np[0][j], frames_np[0][j + 1], return_iters=True)
+            log = eng.tvl1_pair_stats(j)
+            parity = {"aee_px": synth.aee(got, ref), "max_abs_px": float(np.abs(got - ref).max()), "pair": j, "against": "oracle/tvl1_oracle.c (CPU restatement, parity unpinned: no TV-L1 binary exists in this image)",
+                      "iterations_engine": int(log.sum()), "iterations_oracle": int(ref_log.sum()),
+                      "iteration_log_equal": bool(np.array_equal(log, ref_log)), "tolerance_px": 0.01}
+        else:
+            ref = O.farn_calc(frames_np[0][j], frames_np[0][j + 1])
+            parity = {"aee_px": synth.aee(got, ref), "max_abs_px": float(np.abs(got - ref).max()), "pair": j,
+                      "against": "oracle/farneback_oracle.c (pinned to cv2.calcOpticalFlowFarneback)", "tolerance_px": 0.01}
+
     # ---------------- cpu baseline: bounded sample of the same workload on the host cores -----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,11 +445,7 @@ def main():
             "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_dev_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "algorithm": alg, "width": W, "height": H, "step": 1, "pairs_per_step": P,
-                       "frames_per_step": n_frames, "sharding": "one independent frame stream per rank, no collective",
-                       "l2": "no explicit flush: per-pair working set (16 fp32 planes x 5 levels, ~0.3 GB x lanes) exceeds the 126 MB L2 "
-                             "and consecutive steps alternate between two input windows",
-                       "aee_tolerance_px": 0.01},
+            "config": bench_config(args, alg, W, H, desc),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": n_frames * W * H,
                     "d2h_bytes_per_step": P * W * H * 8, "ms_per_step": dt_host_max / args.steps * 1e3,
                     "call": "dfb_calc_batch_host (pinned host frames in, pinned host CV_32FC2 flows out)"},
@@ -403,6 +455,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if parity:
+            line["parity_aee_px"] = parity["aee_px"]
+            line["parity"] = parity
         if roof:
             line["roofline"] = roof
         if kernels:

@@ -10,6 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATHS = {
     "default": os.path.join(_HERE, "lib", "libdenseflow_b200.so"),
     "strict": os.path.join(_HERE, "lib", "libdenseflow_b200_strict.so"),
+    # geometry experiments (denseflow_b200/build.py VARIANTS), built on request only
+    "t256": os.path.join(_HERE, "lib", "libdenseflow_b200_t256.so"),
+    "t512": os.path.join(_HERE, "lib", "libdenseflow_b200_t512.so"),
 }
 
 DFB_OK = 0
@@ -31,6 +34,22 @@ class Counters(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("timed_kernel_launches", C.c_uint64),
                 ("timed_kernel_ns", C.c_uint64), ("timed_kernel_pairs", C.c_uint64), ("pixel_chunks", C.c_uint64)]
 
+
+LIST_MAX_WORKERS = 32
+
+
+class Clip(C.Structure):
+    _fields_ = [("frames", C.POINTER(C.c_void_p)), ("n_frames", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class ListStats(C.Structure):
+    _fields_ = [("clips", C.c_uint64), ("flows", C.c_uint64), ("frames", C.c_uint64), ("seconds", C.c_double), ("workers", C.c_int),
+                ("clips_per_worker", C.c_uint64 * LIST_MAX_WORKERS), ("flows_per_worker", C.c_uint64 * LIST_MAX_WORKERS),
+                ("busy_seconds_per_worker", C.c_double * LIST_MAX_WORKERS), ("finish_seconds_per_worker", C.c_double * LIST_MAX_WORKERS)]
+
+
+CHUNK_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                            C.POINTER(C.c_void_p))
 
 # every symbol include/denseflow_b200.h declares, with its signature
 SIGNATURES = {
@@ -65,9 +84,16 @@ SIGNATURES = {
                                        C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]),
     "dfb_debug_time_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "dfb_get_tvl1_stats": (C.c_int, [C.c_void_p, C.POINTER(Tvl1Stats)]),
+    "dfb_get_tvl1_pair_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Tvl1Stats)]),
     "dfb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "dfb_get_tvl1_phase_ns": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "dfb_reset_counters": (C.c_int, [C.c_void_p]),
+    "dfb_queue_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "dfb_queue_next": (C.c_long, [C.c_void_p]),
+    "dfb_queue_reset": (None, [C.c_void_p]),
+    "dfb_queue_close": (None, [C.c_void_p, C.c_int]),
+    "dfb_run_list": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(Clip), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.POINTER(ListStats), C.c_char_p, C.c_size_t]),
 }
 
 _libs = {}

@@ -69,8 +69,9 @@ class DenseOpticalFlow:
             self._check(self._L.dfb_calc_host(self._h, a.ctypes.data, b.ctypes.data, w, h, flow.ctypes.data))
             return flow
         import torch
-        if a.dtype != torch.uint8 or a.dim() != 2 or a.shape != b.shape or not a.is_cuda:
-            raise RuntimeError("calc: frames must be two CV_8UC1 CUDA tensors of the same size")
+        if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.dim() != 2 or a.shape != b.shape or not a.is_cuda or not b.is_cuda \
+                or a.stride(1) != 1 or b.stride(1) != 1:
+            raise RuntimeError("calc: frames must be two CV_8UC1 CUDA tensors of the same size with unit column stride")
         h, w = a.shape
         if flow is None:
             flow = torch.empty((h, w, 2), dtype=torch.float32, device=a.device)
@@ -79,12 +80,29 @@ class DenseOpticalFlow:
                                             flow.data_ptr(), flow.stride(0) * 4, C.c_void_p(s)))
         return flow
 
+    @staticmethod
+    def _gray_frames(frames):
+        """Every frame must be a CV_8UC1 image of the first frame's size (the C side reads width*height bytes of each)."""
+        out = []
+        for i, f in enumerate(frames):
+            f = np.asarray(f)
+            if f.dtype != np.uint8 or f.ndim != 2 or (out and f.shape != out[0].shape):
+                raise RuntimeError("frame %d: expected a uint8 [H,W] image of the same size as frame 0" % i)
+            out.append(np.ascontiguousarray(f))
+        return out
+
+    @staticmethod
+    def _check_out(a, shape, dtype, name):
+        if not isinstance(a, np.ndarray) or a.dtype != dtype or a.shape[1:] != tuple(shape[1:]) or a.shape[0] < shape[0] \
+                or not all(a[i].flags.c_contiguous for i in range(shape[0])):
+            raise RuntimeError("%s: expected a C-contiguous %s array of shape %s" % (name, np.dtype(dtype).name, tuple(shape)))
+
     # -- the batch shape of calc_optflows_imp (src/denseflow_gpu.cpp:307-342) --
     def calc_batch(self, frames, step=1, flows=None, bound=None):
         """frames: sequence of uint8 [H,W] host arrays (or one [N,H,W] array).  Returns M = max(N-|step|,0)
         flows [M,H,W,2] float32, or with bound=B the quantised (qx, qy) uint8 [M,H,W] planes
         (convertFlowToImage, src/common.cpp:4-16, done on the GPU)."""
-        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        frames = self._gray_frames(frames)
         n = len(frames)
         if n == 0:
             return np.empty((0, 0, 0, 2), np.float32)
@@ -94,6 +112,7 @@ class DenseOpticalFlow:
         if bound is None:
             if flows is None:
                 flows = np.empty((m, h, w, 2), np.float32)
+            self._check_out(flows, (m, h, w, 2), np.float32, "flows")
             op = (C.c_void_p * max(m, 1))(*[flows[i].ctypes.data for i in range(m)])
             self._check(self._L.dfb_calc_batch_host(self._h, fp, n, step, w, h, op))
             return flows
@@ -106,10 +125,12 @@ class DenseOpticalFlow:
 
     def calc_batch_u8_into(self, frames, step, bound, qx, qy):
         """calc_batch(..., bound=B) writing into caller-provided (e.g. pinned) uint8 arrays qx, qy of shape [M,H,W]."""
-        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        frames = self._gray_frames(frames)
         n = len(frames)
         h, w = frames[0].shape
         m = max(n - abs(step), 0)
+        self._check_out(qx, (m, h, w), np.uint8, "qx")
+        self._check_out(qy, (m, h, w), np.uint8, "qy")
         fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
         xp = (C.c_void_p * max(m, 1))(*[qx[i].ctypes.data for i in range(m)])
         yp = (C.c_void_p * max(m, 1))(*[qy[i].ctypes.data for i in range(m)])
@@ -173,6 +194,8 @@ class DenseOpticalFlow:
         """frames_bgr: list of uint8 [H,W,3]; new_size: (w, h) or None.  Returns [(jpg_x bytes, jpg_y bytes)] per pair."""
         frames = [np.ascontiguousarray(f, np.uint8) for f in frames_bgr]
         n = len(frames)
+        if any(f.ndim != 3 or f.shape != frames[0].shape or f.shape[2] != 3 for f in frames):
+            raise RuntimeError("process_bgr_batch: frames must be uint8 [H,W,3] images of one size")
         sh, sw = frames[0].shape[:2]
         dw, dh = new_size if new_size else (0, 0)
         ow, oh = (dw, dh) if new_size else (sw, sh)
@@ -216,6 +239,12 @@ class DenseOpticalFlow:
         iters = flat[:st.nscales * st.warps].reshape(st.nscales, st.warps)
         sizes = [(st.level_w[i], st.level_h[i]) for i in range(st.nscales)]
         return iters, sizes
+
+    def tvl1_pair_stats(self, pair_index):
+        """Executed inner iterations [nscales, warps] of pair `pair_index` of the most recent calc / batch call."""
+        st = _lib.Tvl1Stats()
+        self._check(self._L.dfb_get_tvl1_pair_stats(self._h, int(pair_index), C.byref(st)))
+        return np.array(st.iters[:], np.int64)[:st.nscales * st.warps].reshape(st.nscales, st.warps)
 
     def counters(self):
         c = _lib.Counters()

@@ -21,6 +21,9 @@ VARIANTS = {
     "default": ("libdenseflow_b200.so", []),
     # IEEE arithmetic, no FMA contraction: used by tests to separate restatement bugs from fp noise
     "strict": ("libdenseflow_b200_strict.so", ["-DDFB_STRICT_FP", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
+    # geometry experiments of the fused tvl1 kernel (not built by default): python -m denseflow_b200.build t256
+    "t256": ("libdenseflow_b200_t256.so", ["-DDFB_FUSED_THREADS=256"]),
+    "t512": ("libdenseflow_b200_t512.so", ["-DDFB_FUSED_THREADS=512"]),
 }
 
 
@@ -72,4 +75,5 @@ def build(variants=("default", "strict"), verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print("\n".join(build(verbose="-v" in sys.argv, force="-f" in sys.argv)))
+    names = tuple(a for a in sys.argv[1:] if a in VARIANTS) or ("default", "strict")
+    print("\n".join(build(names, verbose="-v" in sys.argv, force="-f" in sys.argv)))

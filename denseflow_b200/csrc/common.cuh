@@ -33,6 +33,18 @@ inline void check(cudaError_t e, const char *what, const char *file, int line) {
 #define DFB_CUDA(x) ::dfb::check((x), #x, __FILE__, __LINE__)
 #define DFB_KERNEL_CHECK() ::dfb::check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
+// convertFlowToImage, /root/reference/src/common.cpp:4-16: the CAST macro evaluates in double (the bounds are double),
+// left to right, then cvRound (round-half-to-even).  Shared by the stand-alone quantiser and the merge epilogues.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint8_t quantise_px(float v, double L, double H) {
+    if ((double)v > H) return 255;
+    if ((double)v < L) return 0;
+    const double q = 255 * ((double)v - L) / (H - L);
+    if (q != q) return 0;
+    return (uint8_t)__double2int_rn(q);
+}
+#endif
+
 // Bump allocator over one cudaMalloc slab: all engine workspace is carved out at create time
 // (180 GB of HBM3e: no allocation ever happens on the per-pair path).
 class Slab {

@@ -62,26 +62,41 @@ int fail(dfb_handle *h, int code, const std::string &msg) {
     return code;
 }
 
+// after a failure in the middle of a call no copy into a caller buffer may still be in flight when the call returns
+void quiesce(dfb_handle *h) {
+    if (!h) return;
+    for (cudaStream_t s : {h->s_in, h->s_compute, h->s_out})
+        if (s) cudaStreamSynchronize(s);
+    cudaGetLastError();
+}
+
 template <typename F> int guarded(dfb_handle *h, F &&f) {
     try {
         return f();
     } catch (const CudaError &e) {
+        quiesce(h);
         return fail(h, DFB_ERR_CUDA, e.what());
     } catch (const std::exception &e) {
+        quiesce(h);
         return fail(h, DFB_ERR_INVALID_ARG, e.what());
     } catch (...) {
+        quiesce(h);
         return fail(h, DFB_ERR_INVALID_ARG, "unknown exception");
     }
 }
 
-bool is_pinned_or_device(const void *p) {
+// 1: page-locked (or managed) host memory the copy engines can reach directly; 0: pageable host memory (staged through
+// the handle's pinned ring); -1: a device pointer, which the host entry points reject
+int host_pointer_kind(const void *p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return 0;
     }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    if (a.type == cudaMemoryTypeDevice) return -1;
+    return (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
+bool is_pinned_host(const void *p) { return host_pointer_kind(p) == 1; }
 
 int check_size(dfb_handle *h, int w, int h_) {
     if (w <= 0 || h_ <= 0) return fail(h, DFB_ERR_INVALID_ARG, "width/height must be positive");
@@ -136,8 +151,17 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
     const int astep = std::abs(step);
     const int M = std::max(n_frames - astep, 0);  // :308
     if (M == 0) return DFB_OK;
+    for (int f = 0; f < n_frames; ++f)
+        if (!frames[f] || host_pointer_kind(frames[f]) < 0)
+            return fail(h, DFB_ERR_INVALID_ARG, "frames[" + std::to_string(f) + "] is null or a device pointer (host entry point: use dfb_calc_batch_device)");
+    for (int j = 0; j < M; ++j) {
+        const void *o0 = bound > 0 ? (const void *)qx[j] : (const void *)flows[j], *o1 = bound > 0 ? (const void *)qy[j] : o0;
+        if (!o0 || !o1 || host_pointer_kind(o0) < 0 || host_pointer_kind(o1) < 0)
+            return fail(h, DFB_ERR_INVALID_ARG, "output " + std::to_string(j) + " is null or a device pointer (host entry point)");
+    }
     ensure_host_path(h);
     FlowAlgorithm &alg = *h->alg;
+    alg.begin_batch();
     // pairs per solve_batch call; the frame slots hold one group plus the look-ahead frame
     const int B = std::max(1, std::min(alg.max_concurrent_pairs(w, hh), dfb_handle::kFlowRing / 2));
     alg.ensure_slots(B + astep + 1);
@@ -151,7 +175,7 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             const int f = uploaded, r = f % FR;
             if (f >= FR) DFB_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_pyr[r], 0));  // ring slot's pyramid is built
             const uint8_t *src = frames[f];
-            if (!is_pinned_or_device(src)) {
+            if (!is_pinned_host(src)) {
                 // the pinned staging buffer of this ring slot is free once its previous H2D finished
                 if (f >= FR) DFB_CUDA(cudaEventSynchronize(h->ev_in[r]));
                 std::memcpy(stage_frame(h, r), src, fbytes);
@@ -193,30 +217,33 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             const int ring = j % OR;
             drain(ring);
             if (j >= OR) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_out[ring], 0));  // device output slot is free
-            jobs[i] = FlowAlgorithm::PairJob{a % nslots, b % nslots, h->d_flow[ring], (size_t)w * 2 * sizeof(float)};
-        }
-        alg.solve_batch(jobs.data(), m, w, hh, h->s_compute);
-        for (int i = 0; i < m; ++i) {
-            const int j = j0 + i, ring = j % OR;
-            if (bound > 0) {
-                launch_quantise(h->d_flow[ring], (size_t)w * 2 * sizeof(float), w, hh, bound, h->d_qx[ring], h->d_qy[ring], w,
-                                h->s_compute);
-                ++alg.launches;
+            FlowAlgorithm::PairJob &pj = jobs[i];
+            pj = FlowAlgorithm::PairJob{};
+            pj.slot_a = a % nslots;
+            pj.slot_b = b % nslots;
+            pj.flow_xy = h->d_flow[ring];
+            pj.flow_pitch_bytes = (size_t)w * 2 * sizeof(float);
+            if (bound > 0) {  // f1: the engine's merge epilogue writes the two uint8 planes directly
+                pj.bound = bound;
+                pj.qx = h->d_qx[ring];
+                pj.qy = h->d_qy[ring];
+                pj.q_pitch = (size_t)w;
             }
         }
+        alg.solve_batch(jobs.data(), m, w, hh, h->s_compute);
         DFB_CUDA(cudaEventRecord(h->ev_done[j0 % OR], h->s_compute));
         DFB_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[j0 % OR], 0));
         for (int i = 0; i < m; ++i) {
             const int j = j0 + i, ring = j % OR;
             if (bound > 0) {
-                const bool direct = is_pinned_or_device(qx[j]) && is_pinned_or_device(qy[j]);
+                const bool direct = is_pinned_host(qx[j]) && is_pinned_host(qy[j]);
                 uint8_t *dx = direct ? qx[j] : stage_q(h, ring), *dy = direct ? qy[j] : stage_q(h, ring) + fbytes;
                 DFB_CUDA(cudaMemcpyAsync(dx, h->d_qx[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
                 DFB_CUDA(cudaMemcpyAsync(dy, h->d_qy[ring], fbytes, cudaMemcpyDeviceToHost, h->s_out));
                 if (!direct) pending_copy[ring] = j;
                 h->counters.d2h_bytes += 2 * fbytes;
             } else {
-                const bool direct = is_pinned_or_device(flows[j]);
+                const bool direct = is_pinned_host(flows[j]);
                 DFB_CUDA(cudaMemcpyAsync(direct ? flows[j] : stage_flow(h, ring), h->d_flow[ring], fbytes * 2 * sizeof(float),
                                          cudaMemcpyDeviceToHost, h->s_out));
                 if (!direct) pending_copy[ring] = j;
@@ -342,9 +369,12 @@ int dfb_calc_device(dfb_handle *h, const uint8_t *a, size_t a_pitch, const uint8
     if (int rc = check_size(h, width, height)) return rc;
     if (a_pitch < (size_t)width || b_pitch < (size_t)width || flow_pitch < (size_t)width * 8)
         return fail(h, DFB_ERR_INVALID_ARG, "pitch smaller than a row");
+    if ((reinterpret_cast<uintptr_t>(flow_xy) | flow_pitch) & 7)
+        return fail(h, DFB_ERR_INVALID_ARG, "flow_xy and flow_pitch must be 8-byte aligned (CV_32FC2 rows)");
     return guarded(h, [&]() {
         DFB_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        h->alg->begin_batch();
         h->alg->prepare_frame(a, a_pitch, width, height, 0, s);
         h->alg->prepare_frame(b, b_pitch, width, height, 1, s);
         h->alg->solve(0, 1, width, height, flow_xy, flow_pitch, s);
@@ -398,6 +428,7 @@ int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, in
         DFB_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         FlowAlgorithm &alg = *h->alg;
+        alg.begin_batch();
         const int B = std::max(1, alg.max_concurrent_pairs(width, height));
         alg.ensure_slots(B + astep + 1);
         const int nslots = alg.num_slots();
@@ -412,7 +443,11 @@ int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, in
                 const int j = j0 + i;
                 const int a = step > 0 ? j : j + astep;
                 const int b = step > 0 ? j + astep : j;
-                jobs[i] = FlowAlgorithm::PairJob{a % nslots, b % nslots, flows + (size_t)j * fbytes * 2, (size_t)width * 8};
+                jobs[i] = FlowAlgorithm::PairJob{};
+                jobs[i].slot_a = a % nslots;
+                jobs[i].slot_b = b % nslots;
+                jobs[i].flow_xy = flows + (size_t)j * fbytes * 2;
+                jobs[i].flow_pitch_bytes = (size_t)width * 8;
             }
             alg.solve_batch(jobs.data(), m, width, height, s);
             h->counters.pairs += m;
@@ -427,6 +462,9 @@ int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, 
     if (!flow_xy || !qx || !qy) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
     if (bound <= 0) return fail(h, DFB_ERR_INVALID_ARG, "bound should > 0!");
     if (width <= 0 || height <= 0) return fail(h, DFB_ERR_INVALID_ARG, "width/height must be positive");
+    if (flow_pitch < (size_t)width * 8 || q_pitch < (size_t)width) return fail(h, DFB_ERR_INVALID_ARG, "pitch smaller than a row");
+    if ((reinterpret_cast<uintptr_t>(flow_xy) | flow_pitch) & 7)
+        return fail(h, DFB_ERR_INVALID_ARG, "flow_xy and flow_pitch must be 8-byte aligned (CV_32FC2 rows)");
     return guarded(h, [&]() {
         DFB_CUDA(cudaSetDevice(h->device));
         launch_quantise(flow_xy, flow_pitch, width, height, bound, qx, qy, q_pitch, static_cast<cudaStream_t>(stream));
@@ -700,6 +738,15 @@ int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out) {
         DFB_CUDA(cudaSetDevice(h->device));
         h->alg->tvl1_stats(out);
         return DFB_OK;
+    });
+}
+
+int dfb_get_tvl1_pair_stats(dfb_handle *h, int pair_index, dfb_tvl1_stats *out) {
+    if (!h || !out) return DFB_ERR_INVALID_ARG;
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        if (!h->alg->pair_stats(pair_index, out)) return fail(h, DFB_ERR_INVALID_ARG, "pair_index is not one of the last 256 pairs of the most recent tvl1 batch call");
+        return (int)DFB_OK;
     });
 }
 

@@ -37,6 +37,12 @@ class FlowAlgorithm {
         int slot_a, slot_b;
         float *flow_xy;
         size_t flow_pitch_bytes;
+        // bound > 0: the merge epilogue writes convertFlowToImage's two uint8 planes (src/common.cpp:4-16, bounds -bound /
+        // +bound) to qx / qy (row pitch q_pitch bytes) INSTEAD of the float2 field; flow_xy may then be null
+        // for the fused tvl1 and Farneback engines (the unfused tvl1 schedule still needs it as scratch)
+        int bound = 0;
+        uint8_t *qx = nullptr, *qy = nullptr;
+        size_t q_pitch = 0;
     };
     virtual int max_concurrent_pairs(int w, int h) { (void)w; (void)h; return 1; }
     virtual void solve_batch(const PairJob *jobs, int n, int w, int h, cudaStream_t s) {
@@ -45,6 +51,9 @@ class FlowAlgorithm {
     virtual bool set_param(const std::string &name, double v) = 0;
     virtual bool get_param(const std::string &name, double *v) const = 0;
     virtual void tvl1_stats(dfb_tvl1_stats *out) { *out = dfb_tvl1_stats{}; }
+    // per-pair iteration logs of the most recent batch call: begin_batch() restarts the numbering
+    virtual void begin_batch() {}
+    virtual bool pair_stats(int pair_index, dfb_tvl1_stats *out) { (void)pair_index; *out = dfb_tvl1_stats{}; return false; }
     virtual void phase_ns(uint64_t *out) { for (int i = 0; i < 32; ++i) out[i] = 0; }
     virtual void reset_counters() { launches = 0; pixel_iters = 0; pixel_chunks = 0; }
     virtual void kernel_timing(uint64_t *launches_, uint64_t *ns, uint64_t *pairs) { *launches_ = *ns = *pairs = 0; }

@@ -231,6 +231,9 @@ struct PairArgs {
     Plane pfx, pfy;  // previous (coarser) level's flow
     float *flow_xy;
     size_t flow_pitch_bytes;
+    int bound;  // > 0: the merge writes the two quantised uint8 planes instead (PairJob)
+    uint8_t *qx, *qy;
+    size_t q_pitch;
 };
 struct FarnBatchArgs {
     PairArgs p[kMaxFarnBatch];
@@ -406,8 +409,14 @@ __global__ void __launch_bounds__(256) k_farn_merge(const __grid_constant__ Farn
     const PairArgs &a = args.p[blockIdx.z];
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= a.fx.w || y >= a.fx.h) return;
+    const float u = a.fx.p[(size_t)y * a.fx.pitch + x], v = a.fy.p[(size_t)y * a.fy.pitch + x];
+    if (a.bound > 0) {  // convertFlowToImage (src/common.cpp:4-16) as the epilogue
+        a.qx[(size_t)y * a.q_pitch + x] = quantise_px(u, -(double)a.bound, (double)a.bound);
+        a.qy[(size_t)y * a.q_pitch + x] = quantise_px(v, -(double)a.bound, (double)a.bound);
+        return;
+    }
     float2 *row = reinterpret_cast<float2 *>(reinterpret_cast<char *>(a.flow_xy) + (size_t)y * a.flow_pitch_bytes);
-    row[x] = make_float2(a.fx.p[(size_t)y * a.fx.pitch + x], a.fy.p[(size_t)y * a.fy.pitch + x]);
+    row[x] = make_float2(u, v);
 }
 
 constexpr size_t kBoxSmemBytes = (size_t)(5 * (BH + 12) * (BW + 12) + 5 * BH * (BW + 12)) * sizeof(float);
@@ -610,7 +619,11 @@ class Farneback final : public FlowAlgorithm {
 
     // per-pair work (B.4, B.5): coarse -> fine, 10 fused box / solve / rebuild iterations per level
     void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes, cudaStream_t s) override {
-        const PairJob one{slot_a, slot_b, flow_xy, flow_pitch_bytes};
+        PairJob one{};
+        one.slot_a = slot_a;
+        one.slot_b = slot_b;
+        one.flow_xy = flow_xy;
+        one.flow_pitch_bytes = flow_pitch_bytes;
         solve_batch(&one, 1, w, h, s);
     }
     int max_concurrent_pairs(int, int) override { return kMaxFarnBatch; }
@@ -640,6 +653,10 @@ class Farneback final : public FlowAlgorithm {
                     }
                     a.flow_xy = jobs[j0 + i].flow_xy;
                     a.flow_pitch_bytes = jobs[j0 + i].flow_pitch_bytes;
+                    a.bound = jobs[j0 + i].bound;
+                    a.qx = jobs[j0 + i].qx;
+                    a.qy = jobs[j0 + i].qy;
+                    a.q_pitch = jobs[j0 + i].q_pitch;
                 }
                 const dim3 g8(ceil_div(L.w, 32), ceil_div(L.h, 8), nb), b8(32, 8);
                 float rfx = 1.f, rfy = 1.f;

@@ -23,11 +23,12 @@ __device__ __forceinline__ float f_rcp(float a) {
     return r;
 }
 __device__ __forceinline__ float f_div(float a, float b) { return a * f_rcp(b); }
-__device__ __forceinline__ float f_hypot(float a, float b) {
-    float r, s = fmaf(a, a, b * b);
+__device__ __forceinline__ float f_sqrt(float s) {
+    float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
     return r;
 }
+__device__ __forceinline__ float f_hypot(float a, float b) { return f_sqrt(fmaf(a, a, b * b)); }
 #endif
 
 struct Tvl1Consts {

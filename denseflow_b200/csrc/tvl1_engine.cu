@@ -22,6 +22,7 @@ namespace dfb {
 namespace {
 
 constexpr int kMaxScales = 16;
+constexpr double kAllocScaleStep = 0.8;  // scaleStep the slot / lane pyramid layout is sized for (the create() default)
 
 struct Tvl1Params {
     double tau = 0.25, lambda = 0.15, theta = 0.3;
@@ -30,11 +31,10 @@ struct Tvl1Params {
     int iterations = 300;
     double scale_step = 0.8;
     int fused = 1;
-    int fused_k = 8;
+    int fused_k = kFusedDefaultK;
     int flag_sync = 1;
     int time_kernels = 0;
     int use_tma = 1;
-    int cluster = 1;  // 2: thread-block clusters of two CTAs share a 128 x 128 region (needs flag_sync and use_tma)
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
@@ -53,6 +53,7 @@ class Tvl1 final : public FlowAlgorithm {
             if (l.tmaps) cudaFree(l.tmaps);
         }
         if (stats_event_) cudaEventDestroy(stats_event_);
+        if (pair_log_) cudaFreeHost(pair_log_);
     }
     const char *name() const override { return "tvl1"; }
     int num_slots() const override { return (int)slots_.size(); }
@@ -61,6 +62,10 @@ class Tvl1 final : public FlowAlgorithm {
         while ((int)slots_.size() < n) {
             float *p = nullptr;
             DFB_CUDA(cudaMalloc(&p, pyr_elems_ * sizeof(float)));
+            // planes start finite: padding columns are read (never used).  The memset runs on the null stream, which the
+            // handle's non-blocking streams do not wait for: finish it before any of them can touch the slot.
+            DFB_CUDA(cudaMemset(p, 0, pyr_elems_ * sizeof(float)));
+            DFB_CUDA(cudaDeviceSynchronize());
             extra_slots_.push_back(p);
             slots_.push_back(p);
         }
@@ -74,13 +79,16 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "warps") { if (v < 1 || v > 16) return false; prm_.warps = (int)v; }
         else if (k == "epsilon") prm_.epsilon = v;
         else if (k == "iterations") { if (v < 1) return false; prm_.iterations = (int)v; }
-        else if (k == "scale_step") { if (!(v > 0 && v < 1)) return false; prm_.scale_step = v; }
+        else if (k == "scale_step") {
+            // the pyramid slots were laid out at create time for the default 0.8: a larger factor would not fit them
+            if (!(v > 0 && v <= kAllocScaleStep)) return false;
+            prm_.scale_step = v;
+        }
         else if (k == "fused") prm_.fused = v != 0;
-        else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK) return false; prm_.fused_k = (int)v; }
+        else if (k == "fused_k") { if (v < 1 || v > kFusedMaxK || 2 * v >= kFusedTileH) return false; prm_.fused_k = (int)v; }
         else if (k == "flag_sync") prm_.flag_sync = (int)v;  // 0 CTA barriers, 1 spin on neighbour flags, n > 1: spin with n ns back-off
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "use_tma") prm_.use_tma = v != 0;
-        else if (k == "cluster") { if (v != 1 && v != 2) return false; prm_.cluster = (int)v; }
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -99,7 +107,6 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "flag_sync") *v = prm_.flag_sync;
         else if (k == "time_kernels") *v = prm_.time_kernels;
         else if (k == "use_tma") *v = prm_.use_tma;
-        else if (k == "cluster") *v = prm_.cluster;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -139,7 +146,11 @@ class Tvl1 final : public FlowAlgorithm {
         last_nscales_ = n;
         std::memcpy(last_lv_, lv, sizeof(lv));
         if (prm_.fused) {
-            const PairJob one{slot_a, slot_b, flow_xy, flow_pitch_bytes};
+            PairJob one{};
+            one.slot_a = slot_a;
+            one.slot_b = slot_b;
+            one.flow_xy = flow_xy;
+            one.flow_pitch_bytes = flow_pitch_bytes;
             solve_fused(&one, 1, lv, n, s);
         } else {
             solve_unfused(slot_a, slot_b, lv, n, flow_xy, flow_pitch_bytes, s);
@@ -154,7 +165,7 @@ class Tvl1 final : public FlowAlgorithm {
         if (prm_.lanes > 0) return prm_.lanes;
         LevelGeom lv[kMaxScales];
         const int n = level_geometry(w, h, lv);
-        const int sms = fused_num_sms(device_);
+        const int sms = fused_cta_slots(device_);
         const int hy = prm_.fused_k, hx = (hy + 3) & ~3;
         int best = 1;
         double best_u = -1;
@@ -164,8 +175,7 @@ class Tvl1 final : public FlowAlgorithm {
             double num = 0, den = 0;
             for (int l = 0; l < n; ++l) {
                 const double wgt = l == n - 1 ? 7.0 : (l == n - 2 ? 1.5 : 1.0);
-                const int cs = effective_cluster();
-                const int tiles = cs * fused_tiles_along(lv[l].w, kFusedTileW, hx) * fused_tiles_along(lv[l].h, kFusedTileH * cs, hy);
+                const int tiles = fused_tiles_along(lv[l].w, kFusedTileW, hx) * fused_tiles_along(lv[l].h, kFusedTileH, hy);
                 const int rounds = (tiles + G - 1) / G;
                 num += wgt * tiles;
                 den += wgt * (double)rounds * G;
@@ -179,16 +189,21 @@ class Tvl1 final : public FlowAlgorithm {
         return best;
     }
 
-    int effective_cluster() const { return (prm_.cluster == 2 && prm_.flag_sync && prm_.use_tma) ? 2 : 1; }
-
     void solve_batch(const PairJob *jobs, int count, int w, int h, cudaStream_t s) override {
         LevelGeom lv[kMaxScales];
         const int n = level_geometry(w, h, lv);
         last_nscales_ = n;
         std::memcpy(last_lv_, lv, sizeof(lv));
         if (!prm_.fused) {
-            for (int i = 0; i < count; ++i)
+            for (int i = 0; i < count; ++i) {
+                if (!jobs[i].flow_xy) throw std::runtime_error("tvl1 (fused = 0): the float2 flow buffer is needed as scratch");
                 solve_unfused(jobs[i].slot_a, jobs[i].slot_b, lv, n, jobs[i].flow_xy, jobs[i].flow_pitch_bytes, s);
+                if (jobs[i].bound > 0) {  // the reference's structure: a separate pass over the finished field
+                    launch_quantise(jobs[i].flow_xy, jobs[i].flow_pitch_bytes, lv[0].w, lv[0].h, jobs[i].bound, jobs[i].qx, jobs[i].qy,
+                                    jobs[i].q_pitch, s);
+                    ++launches;
+                }
+            }
             return;
         }
         const int B = std::min(max_concurrent_pairs(w, h), kFusedMaxLanes);
@@ -203,7 +218,7 @@ class Tvl1 final : public FlowAlgorithm {
         *out = dfb_tvl1_stats{};
         if (stats_pending_) {  // fused engine: the log was written by the kernel into mapped host memory
             DFB_CUDA(cudaEventSynchronize(stats_event_));
-            for (int i = 0; i < 16 * 16; ++i) last_iters_[i] = lanes_[last_lane_].host_ctl->iters[i];
+            std::memcpy(last_iters_, pair_log_ + (size_t)last_log_slot_ * kLogInts, sizeof(last_iters_));
             stats_pending_ = false;
         }
         pixel_iters = unfused_px_iters_;
@@ -221,7 +236,27 @@ class Tvl1 final : public FlowAlgorithm {
         std::memcpy(out->iters, last_iters_, sizeof(last_iters_));
     }
 
+    void begin_batch() override { pair_log_count_ = 0; }
+    bool pair_stats(int idx, dfb_tvl1_stats *out) override {
+        *out = dfb_tvl1_stats{};
+        if (idx < 0 || idx >= pair_log_count_ || idx < pair_log_count_ - kPairLog) return false;
+        if (stats_pending_) DFB_CUDA(cudaEventSynchronize(stats_event_));
+        out->nscales = last_nscales_;
+        out->warps = prm_.warps;
+        for (int s = 0; s < last_nscales_; ++s) {
+            out->level_w[s] = last_lv_[s].w;
+            out->level_h[s] = last_lv_[s].h;
+        }
+        std::memcpy(out->iters, pair_log_ + (size_t)(idx % kPairLog) * kLogInts, sizeof(out->iters));
+        return true;
+    }
+
   private:
+    int next_log_slot() {
+        last_log_slot_ = pair_log_count_ % kPairLog;
+        ++pair_log_count_;
+        return last_log_slot_;
+    }
     Plane level_plane(float *base, const LevelGeom *lv, int l) const {
         size_t off = 0;
         for (int i = 0; i < l; ++i) off += level_stride(i);
@@ -234,6 +269,7 @@ class Tvl1 final : public FlowAlgorithm {
         // geometry of the largest frame, with the full default pyramid depth available
         Tvl1Params keep = prm_;
         prm_.nscales = kMaxScales;
+        prm_.scale_step = kAllocScaleStep;
         LevelGeom lv[kMaxScales];
         const int n = level_geometry(max_w_, max_h_, lv);
         prm_ = keep;
@@ -250,6 +286,9 @@ class Tvl1 final : public FlowAlgorithm {
         for (int i = 0; i < kInitialSlots; ++i) slots_.push_back(slab_.take<float>(pyr_elems_));
         ensure_lanes(1);
         DFB_CUDA(cudaEventCreateWithFlags(&stats_event_, cudaEventDisableTiming));
+        DFB_CUDA(cudaHostAlloc(&pair_log_, sizeof(int) * kLogInts * kPairLog, cudaHostAllocMapped));
+        std::memset(pair_log_, 0, sizeof(int) * kLogInts * kPairLog);
+        DFB_CUDA(cudaHostGetDevicePointer(&pair_log_dev_, pair_log_, 0));
         // every plane starts finite: padding columns are read (never used) by vectorised kernels
         slab_.zero();
     }
@@ -266,6 +305,7 @@ class Tvl1 final : public FlowAlgorithm {
         FusedHostCtl *host_ctl = nullptr, *dev_ctl = nullptr;
         void *tmaps = nullptr;  // device array CUtensorMap[kMaxScales][kFusedMapsPerLevel]
         int tmap_w = 0, tmap_h = 0, tmap_n = 0;
+        double tmap_ss = 0;
     };
 
     void ensure_lanes(int n) {
@@ -275,6 +315,7 @@ class Tvl1 final : public FlowAlgorithm {
             const size_t bytes = 4 * pyr + 14 * pl + Slab::padded(kMaxPartials, 8) + 256;
             DFB_CUDA(cudaMalloc(&l.own, bytes));
             DFB_CUDA(cudaMemset(l.own, 0, bytes));  // planes start finite: padding is read (never used) by vector loads
+            DFB_CUDA(cudaDeviceSynchronize());      // null-stream memset vs the caller's (possibly non-blocking) stream
             char *c = static_cast<char *>(l.own);
             auto take = [&](size_t b) { char *r = c; c += b; return r; };
             for (int b = 0; b < 2; ++b) {
@@ -365,12 +406,13 @@ class Tvl1 final : public FlowAlgorithm {
         launch_merge_flow(level_plane(wk.u1pyr[0], lv, 0), level_plane(wk.u2pyr[0], lv, 0), flow_xy, flow_pitch_bytes, s);
         ++launches;
         stats_pending_ = false;
+        std::memcpy(pair_log_ + (size_t)next_log_slot() * kLogInts, last_iters_, sizeof(last_iters_));
         accumulate_pixel_iters();
     }
 
     // TMA descriptors of the lane's shared-memory-resident planes, rebuilt only when the frame geometry changes
     void ensure_tensor_maps(Lane &wk, const LevelGeom *lv, int n) {
-        if (wk.tmap_w == lv[0].w && wk.tmap_h == lv[0].h && wk.tmap_n == n) return;
+        if (wk.tmap_w == lv[0].w && wk.tmap_h == lv[0].h && wk.tmap_n == n && wk.tmap_ss == prm_.scale_step) return;
         std::vector<char> host((size_t)kMaxScales * kFusedMapsPerLevel * kTensorMapBytes, 0);
         for (int l = 0; l < n; ++l) {
             char *m = host.data() + (size_t)l * kFusedMapsPerLevel * kTensorMapBytes;
@@ -385,6 +427,7 @@ class Tvl1 final : public FlowAlgorithm {
         wk.tmap_w = lv[0].w;
         wk.tmap_h = lv[0].h;
         wk.tmap_n = n;
+        wk.tmap_ss = prm_.scale_step;
     }
 
     // ---- fused = 1 -------------------------------------------------------------------------------
@@ -392,7 +435,7 @@ class Tvl1 final : public FlowAlgorithm {
         ensure_lanes(count);
         FusedBatch batch{};
         batch.njobs = count;
-        batch.group = std::max(1, fused_num_sms(device_) / count);
+        batch.group = std::max(1, fused_cta_slots(device_) / count);
         for (int i = 0; i < count; ++i) {
             Lane &wk = lanes_[i];
             FusedJob &job = batch.job[i];
@@ -434,16 +477,18 @@ class Tvl1 final : public FlowAlgorithm {
             job.partials = wk.partials;
             job.sync = wk.sync;
             job.ctl = wk.dev_ctl;
+            job.iters_log = pair_log_dev_ + (size_t)next_log_slot() * kLogInts;
             job.flow_xy = jobs[i].flow_xy;
             job.flow_pitch_bytes = jobs[i].flow_pitch_bytes;
+            job.bound = jobs[i].bound;
+            job.qx = jobs[i].qx;
+            job.qy = jobs[i].qy;
+            job.q_pitch = jobs[i].q_pitch;
         }
         // one CTA per SM at most: the tile counts of the largest level bound the useful group size
         const int hx = 4, hy = 1;
         const int max_tiles = fused_tiles_along(lv[0].w, kFusedTileW, hx) * fused_tiles_along(lv[0].h, kFusedTileH, hy);
-        const int cs = effective_cluster();
-        batch.cluster = cs;
-        batch.group = std::max(1, std::min(batch.group, cs == 1 ? max_tiles : max_tiles + (max_tiles & 1)));
-        if (cs > 1) batch.group = std::max(cs, batch.group & ~1);  // whole clusters only
+        batch.group = std::max(1, std::min(batch.group, max_tiles));
         if (prm_.time_kernels) {
             if (timing_used_ == kTimingRing) drain_timing();
             if (!timing_ev_[0][0])
@@ -519,6 +564,10 @@ class Tvl1 final : public FlowAlgorithm {
     int timing_used_ = 0;
     uint64_t timed_launches_ = 0, timed_ns_ = 0, timed_pairs_ = 0;
     int last_lane_ = 0;
+    // iteration logs of the last kPairLog pairs, written by the kernel into mapped host memory
+    static constexpr int kPairLog = 256, kLogInts = 16 * 16;
+    int *pair_log_ = nullptr, *pair_log_dev_ = nullptr;
+    int pair_log_count_ = 0, last_log_slot_ = 0;
     cudaEvent_t stats_event_ = nullptr;
     bool stats_pending_ = false;
     int last_nscales_ = 0;

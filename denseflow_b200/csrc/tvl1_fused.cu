@@ -21,8 +21,7 @@
 //
 // Several independent pairs ("lanes") share one launch: lane i runs on CTAs [i*G, (i+1)*G) with its
 // own workspace, barrier words and TMA descriptors, so the coarse scales (fewer tiles than SMs)
-// do not leave SMs idle.  Optionally (cluster = 2) two CTAs of a thread-block cluster stack
-// vertically into a 128 x 128 region and exchange their seam rows through distributed shared memory.
+// do not leave SMs idle.
 //
 // Grid-wide ordering uses a monotonically counting barrier in global memory per lane (all CTAs are
 // co-resident: cooperative launch).  The convergence error is reduced in a fixed order
@@ -187,12 +186,12 @@ __device__ __forceinline__ void phase_warp(const int G, const int bid, const Fus
         tvl1_warp_px(I1, I1x, I1y, W, H, P, x2, y2, u1[o2], u2[o2], __ldg(L.I0 + o2), jx, jy, g2, rc2);
         job.I1wx[o] = ix;
         job.I1wy[o] = iy;
-        job.grad[o] = g;
+        job.grad[o] = tvl1_gq_from_grad(g);  // what the primal step wants of the gradient (tvl1_math.cuh)
         job.rho_c[o] = rc;
         if (has2) {
             job.I1wx[o2] = jx;
             job.I1wy[o2] = jy;
-            job.grad[o2] = g2;
+            job.grad[o2] = tvl1_gq_from_grad(g2);
             job.rho_c[o2] = rc2;
         }
     }
@@ -228,6 +227,16 @@ __device__ __forceinline__ void phase_upsample(const int G, const int bid, const
 // A.5: merge(u1,u2) -> CV_32FC2
 __device__ __forceinline__ void phase_merge(const int G, const int bid, const FusedJob &job, const FusedLevel &L, int cur) {
     const int total = L.h * L.w;
+    if (job.bound > 0) {  // convertFlowToImage as the epilogue: 2 B/px leave the kernel instead of 8
+        const double lo = -(double)job.bound, hi = (double)job.bound;
+        for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
+            const int y = i / L.w, x = i - y * L.w;
+            const size_t o = (size_t)y * L.pitch + x;
+            job.qx[(size_t)y * job.q_pitch + x] = quantise_px(__ldcg(L.u1[cur] + o), lo, hi);
+            job.qy[(size_t)y * job.q_pitch + x] = quantise_px(__ldcg(L.u2[cur] + o), lo, hi);
+        }
+        return;
+    }
     for (int i = bid * kThreads + threadIdx.x; i < total; i += G * kThreads) {
         const int y = i / L.w, x = i - y * L.w;
         const size_t o = (size_t)y * L.pitch + x;
@@ -256,53 +265,152 @@ __device__ __forceinline__ void phase_merge(const int G, const int bid, const Fu
 // the image is overwritten with a copy of the border pixel after every primal step, so the
 // difference is exactly 0 without per-pixel masking; only tiles touching that border pay for it.
 // Returns this thread's share of sum(diff) of the last primal step when `check`.
-__device__ __forceinline__ void wait_ge(const volatile int *flag, int v, unsigned backoff_ns = 0) {
-    while (*flag - v < 0) {
-        if (backoff_ns) __nanosleep(backoff_ns);  // a spinning warp competes for issue slots with the warps it waits for
-    }
-}
-// cluster-scope variants for the two warps on the seam of a 2-CTA cluster tile: the flag lives in the owning CTA's
-// shared memory and is read by the other CTA through DSMEM
-__device__ __forceinline__ void wait_ge_cluster(const int *remote_flag, int v) {
-    if ((threadIdx.x & 31) == 0) {  // one lane polls through DSMEM (~200 cycles per probe); the warp re-converges below
-        int x;
-        do {
-            asm volatile("ld.acquire.cluster.b32 %0, [%1];" : "=r"(x) : "l"(remote_flag) : "memory");
-        } while (x - v < 0);
-    }
-    __syncwarp();
-}
-__device__ __forceinline__ void signal_cluster(int *flag, int v) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) asm volatile("st.release.cluster.b32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+// Poll a neighbour warp's progress counter.  The loads are acquire loads: the (plain) loads of the neighbour's rows that
+// follow must not be moved ahead of the poll — with a volatile poll ptxas hoisted the LDS.128 of the row below above the
+// spin loop (seen in SASS), and results differed run to run.
+__device__ __forceinline__ void wait_ge(const volatile int *flag, int v) {
+    const unsigned addr = smem_u32(const_cast<const int *>(flag));
+    int x;
+    do {
+        asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(x) : "r"(addr) : "memory");
+    } while (x - v < 0);
 }
 __device__ __forceinline__ void signal(volatile int *flag, int v) {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence_block();
-        *flag = v;
-    }
+    if ((threadIdx.x & 31) == 0)  // release store: this warp's rows (ordered before by __syncwarp) are visible before the counter
+        asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(const_cast<const int *>(flag))), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLevel &L, int level, int cur, int tx, int ty,
+// What one thread needs to know about the tile it is working on; everything here is loop-invariant over the kk
+// iterations of a tile visit.
+struct TileCtx {
+    int so0;          // this thread's slot in row 0 of its warp in the shared-memory planes
+    int lane, wq;
+    int base;         // progress-counter value that means "tile loaded"
+    bool flagsync;    // neighbour-warp progress counters (true) or CTA-wide barriers (false, debug / comparison)
+    int jlast, rbot;  // EDGE tiles: pixel j == jlast of this lane is the last image column, row r == rbot of this warp the last image row
+    bool edge_x, edge_y;
+    bool lane_in;     // ERR: this lane's pixels lie in the interior columns of the tile
+    int ry_lo, ry_hi, rows_left;  // ERR: interior rows of the tile, image rows below gy0
+    int cols_left;    // ERR: image columns from gx0 (pixel j counts if j < cols_left)
+};
+
+// One primal + dual iteration of a tile visit.  EDGE: the tile contains the last image column or row (mirror handling
+// for the index-clamped forward differences); ERR: accumulate this thread's share of sum(diff) of the primal step.
+// Interior tiles in the middle of an epoch (the common case) instantiate neither.
+template <bool EDGE, bool ERR>
+__device__ __forceinline__ void tile_iteration(Smem &sm, const TileCtx &t, const Tvl1Consts &c, int it, float4 (&p11)[RPT], float4 (&p12)[RPT],
+                                               float4 (&p21)[RPT], float4 (&p22)[RPT], float &err) {
+    volatile int *prog = sm.prog;
+    const int so0 = t.so0, lane = t.lane, wq = t.wq;
+    // -------- primal: u <- u + d(rho) + theta * div p ------------------------------------------
+    // p above the region's first row: the image border (p = 0) for tile row 0, halo garbage otherwise
+    float4 up12 = zero4(), up22 = zero4();
+    if (wq > 0) {
+        if (t.flagsync) wait_ge(&prog[wq - 1], t.base + 2 * it);
+        up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
+        up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int so = so0 + r * TW;
+        const float4 ix = *reinterpret_cast<const float4 *>(&sm.consts[0][so]);
+        const float4 iy = *reinterpret_cast<const float4 *>(&sm.consts[1][so]);
+        const float4 gq = *reinterpret_cast<const float4 *>(&sm.consts[2][so]);
+        const float4 rc = *reinterpret_cast<const float4 *>(&sm.consts[3][so]);
+        const float4 o1 = *reinterpret_cast<const float4 *>(&sm.u[0][so]);
+        const float4 o2 = *reinterpret_cast<const float4 *>(&sm.u[1][so]);
+        float l11 = __shfl_up_sync(0xffffffffu, p11[r].w, 1);
+        float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
+        if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
+        float4 n1, n2;
+        tvl1_primal_row(ix, iy, gq, rc, o1, o2, p11[r], l11, p12[r], up12, p21[r], l21, p22[r], up22, c, n1, n2);
+        if (ERR) {
+            const int ry = RPT * wq + r;
+            if (t.lane_in && ry >= t.ry_lo && ry < t.ry_hi && r < t.rows_left) {
+                const float4 d = tvl1_diff_row(o1, o2, n1, n2);
+                err += d.x;
+                if (1 < t.cols_left) err += d.y;
+                if (2 < t.cols_left) err += d.z;
+                if (3 < t.cols_left) err += d.w;
+            }
+        }
+        if (EDGE) {
+            if (t.edge_x) {  // mirror the last image column into the pixel right of it: u(x+1) - u(x) == 0 there
+                if (t.jlast == 0) { n1.y = n1.x; n2.y = n2.x; }
+                if (t.jlast == 1) { n1.z = n1.y; n2.z = n2.y; }
+                if (t.jlast == 2) { n1.w = n1.z; n2.w = n2.z; }
+            }
+            if (t.edge_y && r > 0 && r - 1 == t.rbot) {  // first out-of-image row: a copy of the last image row
+                n1 = *reinterpret_cast<const float4 *>(&sm.u[0][so - TW]);
+                n2 = *reinterpret_cast<const float4 *>(&sm.u[1][so - TW]);
+            }
+        }
+        st4(&sm.u[0][so], n1);
+        st4(&sm.u[1][so], n2);
+        up12 = p12[r];
+        up22 = p22[r];
+    }
+    signal(&prog[wq], t.base + 2 * it + 1);
+    if (!t.flagsync) __syncthreads();
+    // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ----------------------------
+    float4 c1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0]);
+    float4 c2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0]);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        float4 d1, d2;
+        if (r < RPT - 1) {
+            d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + (r + 1) * TW]);
+            d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + (r + 1) * TW]);
+        } else {
+            d1 = c1;  // region's last row: halo, or the mirrored image border
+            d2 = c2;
+            if (wq < kWarps - 1) {
+                if (t.flagsync) wait_ge(&prog[wq + 1], t.base + 2 * it + 1);
+                if (!(EDGE && t.edge_y && t.rbot == RPT - 1)) {
+                    d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
+                    d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
+                }
+            }
+        }
+        float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
+        float r2 = __shfl_down_sync(0xffffffffu, c2.x, 1);
+        if (EDGE && t.edge_x && t.jlast == 3) {
+            r1 = c1.w;
+            r2 = c2.w;
+        }
+        tvl1_dual_row(c1, c2, d1, d2, r1, r2, c.taut, p11[r], p12[r], p21[r], p22[r]);
+        c1 = d1;
+        c2 = d2;
+    }
+    st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
+    st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
+    signal(&prog[wq], t.base + 2 * it + 2);
+    if (!t.flagsync) __syncthreads();
+}
+
+template <bool EDGE>
+__device__ __forceinline__ float tile_iterations(Smem &sm, const TileCtx &t, const Tvl1Consts &c, int kk, bool check, float4 (&p11)[RPT],
+                                                 float4 (&p12)[RPT], float4 (&p21)[RPT], float4 (&p22)[RPT]) {
+    float err = 0.f;
+    const int plain = check ? kk - 1 : kk;
+    for (int it = 0; it < plain; ++it) tile_iteration<EDGE, false>(sm, t, c, it, p11, p12, p21, p22, err);
+    if (check) tile_iteration<EDGE, true>(sm, t, c, kk - 1, p11, p12, p21, p22, err);
+    return err;
+}
+
+__device__ __forceinline__ float process_tile(const FusedJob &job, const Tvl1Consts &c, const FusedLevel &L, int level, int cur, int tx, int ty,
                                               int kk, int hx, int hy, bool check, int base, unsigned tma_parity, Smem &sm,
-                                              bool prof_on, int crank, int csize, Smem *sm_above, Smem *sm_below) {
+                                              bool prof_on) {
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     unsigned long long t0 = 0;
     if (prof_on) t0 = gtime();
     const int W = L.w, H = L.h, P = L.pitch;
-    // a cluster of csize CTAs stacked vertically shares one (TH * csize)-row region; this CTA owns rows [TH*crank, TH*crank+TH)
-    const int cth = TH * csize;
-    const int cry0 = ty * (cth - 2 * hy);
-    const int rx0 = tx * (TW - 2 * hx), ry0 = cry0 + TH * crank;
+    const int rx0 = tx * (TW - 2 * hx), ry0 = ty * (TH - 2 * hy);
     const int gx0 = rx0 + 4 * lane;
     const int gy0 = ry0 + RPT * wq;
-    const bool seam_top = crank > 0 && wq == 0;                   // the row above belongs to the CTA above
-    const bool seam_bot = crank < csize - 1 && wq == kWarps - 1;  // the row below belongs to the CTA below
-    const float taut = job.c.taut;
     volatile int *prog = sm.prog;
     const bool flagsync = job.flag_sync != 0;
-    const unsigned backoff = job.flag_sync > 1 ? (unsigned)job.flag_sync : 0u;  // 0: CTA-wide barriers between half-steps (debug / comparison)
 
     float4 p11[RPT], p12[RPT], p21[RPT], p22[RPT];
     const int so0 = (RPT * wq) * TW + 4 * lane;  // this thread's slot in row 0 of its warp (thread-private in smem planes)
@@ -312,10 +420,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         // TMA while every thread loads its share of the four dual planes into registers.  All warps must be done
         // with the previous tile's shared memory first (the bulk copy overwrites every slot).
         fence_proxy_async();
-        if (csize > 1)
-            cooperative_groups::this_cluster().sync();  // the CTA above still reads this CTA's first u row in its last dual step
-        else
-            __syncthreads();
+        __syncthreads();
         if (threadIdx.x == 0) {
             const char *maps = static_cast<const char *>(job.tmaps) + (size_t)level * kFusedMapsPerLevel * kTensorMapBytes;
             mbar_expect_tx(&sm.tma_bar, 6u * kConstPlane * (unsigned)sizeof(float));
@@ -356,135 +461,41 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
         }
     }
     if (use_tma) mbar_wait(&sm.tma_bar, tma_parity);
+    TileCtx t;
+    t.so0 = so0;
+    t.lane = lane;
+    t.wq = wq;
+    t.base = base;
+    t.flagsync = flagsync;
     // image borders inside this tile's region (tile-uniform)
-    const bool edge_x = W - 1 >= rx0 && W - 1 < rx0 + TW;
-    const bool edge_y = H - 1 >= ry0 && H - 1 < ry0 + TH;
-    const int jlast = W - 1 - gx0;  // pixel j == jlast of this lane is the last image column
-    const int rbot = H - 1 - gy0;   // row r == rbot of this warp is the last image row
+    t.edge_x = W - 1 >= rx0 && W - 1 < rx0 + TW;
+    t.edge_y = H - 1 >= ry0 && H - 1 < ry0 + TH;
+    t.jlast = W - 1 - gx0;
+    t.rbot = H - 1 - gy0;
     // which of this thread's pixels are interior (written back / counted in the error)
-    const bool lane_in = (tx == 0 || 4 * lane >= hx) && 4 * lane < TW - hx + (rx0 + TW >= W ? hx : 0) && gx0 < W;
-    const int cy_lo = ty == 0 ? 0 : hy, cy_hi = cth - hy + (cry0 + cth >= H ? hy : 0);  // valid rows of the cluster region
-    const int ry_lo = max(cy_lo - TH * crank, 0), ry_hi = min(cy_hi - TH * crank, TH);
+    t.lane_in = (tx == 0 || 4 * lane >= hx) && 4 * lane < TW - hx + (rx0 + TW >= W ? hx : 0) && gx0 < W;
+    t.ry_lo = ty == 0 ? 0 : hy;
+    t.ry_hi = TH - hy + (ry0 + TH >= H ? hy : 0);
+    t.rows_left = H - gy0;
+    t.cols_left = W - gx0;
 
     // make row RPT-1 of p12/p22 visible to the warp below before the first primal step
     st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
     st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-    if (seam_bot) signal_cluster(&sm.prog[wq], base); else signal(&prog[wq], base);
+    signal(&prog[wq], base);
     if (!flagsync) __syncthreads();
     if (prof_on) {
-        const unsigned long long t = gtime();
-        sm.prof[5] += t - t0;
-        t0 = t;
+        const unsigned long long tt = gtime();
+        sm.prof[5] += tt - t0;
+        t0 = tt;
     }
 
-    float err = 0.f;
-    for (int it = 0; it < kk; ++it) {
-        const bool do_err = check && it == kk - 1;
-        // -------- primal: u <- u + d(rho) + theta * div p --------------------------------------
-        // p above the region's first row: the image border (p = 0) for tile row 0, halo garbage otherwise
-        float4 up12 = zero4(), up22 = zero4();
-        if (wq > 0) {
-            if (flagsync) wait_ge(&prog[wq - 1], base + 2 * it, backoff);
-            up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
-            up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
-        } else if (seam_top) {  // last warp of the CTA above, through distributed shared memory
-            wait_ge_cluster(&sm_above->prog[kWarps - 1], base + 2 * it);
-            up12 = *reinterpret_cast<const float4 *>(&sm_above->p_bot[0][kWarps - 1][4 * lane]);
-            up22 = *reinterpret_cast<const float4 *>(&sm_above->p_bot[1][kWarps - 1][4 * lane]);
-        }
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) {
-            const int so = so0 + r * TW;
-            const float4 ix = *reinterpret_cast<const float4 *>(&sm.consts[0][so]);
-            const float4 iy = *reinterpret_cast<const float4 *>(&sm.consts[1][so]);
-            const float4 g = *reinterpret_cast<const float4 *>(&sm.consts[2][so]);
-            const float4 rc = *reinterpret_cast<const float4 *>(&sm.consts[3][so]);
-            const float4 o1 = *reinterpret_cast<const float4 *>(&sm.u[0][so]);
-            const float4 o2 = *reinterpret_cast<const float4 *>(&sm.u[1][so]);
-            float l11 = __shfl_up_sync(0xffffffffu, p11[r].w, 1);
-            float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
-            if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
-            float4 n1, n2;
-            tvl1_primal_px(ix.x, iy.x, g.x, rc.x, o1.x, o2.x, (p11[r].x - l11) + (p12[r].x - up12.x), (p21[r].x - l21) + (p22[r].x - up22.x), job.c, n1.x, n2.x);
-            tvl1_primal_px(ix.y, iy.y, g.y, rc.y, o1.y, o2.y, (p11[r].y - p11[r].x) + (p12[r].y - up12.y), (p21[r].y - p21[r].x) + (p22[r].y - up22.y), job.c, n1.y, n2.y);
-            tvl1_primal_px(ix.z, iy.z, g.z, rc.z, o1.z, o2.z, (p11[r].z - p11[r].y) + (p12[r].z - up12.z), (p21[r].z - p21[r].y) + (p22[r].z - up22.z), job.c, n1.z, n2.z);
-            tvl1_primal_px(ix.w, iy.w, g.w, rc.w, o1.w, o2.w, (p11[r].w - p11[r].z) + (p12[r].w - up12.w), (p21[r].w - p21[r].z) + (p22[r].w - up22.w), job.c, n1.w, n2.w);
-            if (do_err) {
-                const int ry = RPT * wq + r;
-                if (lane_in && ry >= ry_lo && ry < ry_hi && gy0 + r < H) {
-                    // diff = (u1-u1')^2 + (u2-u2')^2 per pixel (fp32, as the reference's diff plane)
-                    err += (o1.x - n1.x) * (o1.x - n1.x) + (o2.x - n2.x) * (o2.x - n2.x);
-                    if (gx0 + 1 < W) err += (o1.y - n1.y) * (o1.y - n1.y) + (o2.y - n2.y) * (o2.y - n2.y);
-                    if (gx0 + 2 < W) err += (o1.z - n1.z) * (o1.z - n1.z) + (o2.z - n2.z) * (o2.z - n2.z);
-                    if (gx0 + 3 < W) err += (o1.w - n1.w) * (o1.w - n1.w) + (o2.w - n2.w) * (o2.w - n2.w);
-                }
-            }
-            if (edge_x) {  // mirror the last image column into the pixel right of it: u(x+1) - u(x) == 0 there
-                if (jlast == 0) { n1.y = n1.x; n2.y = n2.x; }
-                if (jlast == 1) { n1.z = n1.y; n2.z = n2.y; }
-                if (jlast == 2) { n1.w = n1.z; n2.w = n2.z; }
-            }
-            st4(&sm.u[0][so], n1);
-            st4(&sm.u[1][so], n2);
-            if (edge_y && r > 0 && r - 1 == rbot) {  // first out-of-image row: mirror the last image row into it
-                const float4 m1 = *reinterpret_cast<const float4 *>(&sm.u[0][so - TW]);
-                const float4 m2 = *reinterpret_cast<const float4 *>(&sm.u[1][so - TW]);
-                st4(&sm.u[0][so], m1);
-                st4(&sm.u[1][so], m2);
-            }
-            up12 = p12[r];
-            up22 = p22[r];
-        }
-        if (seam_top) signal_cluster(&sm.prog[wq], base + 2 * it + 1); else signal(&prog[wq], base + 2 * it + 1);
-        if (!flagsync) __syncthreads();
-        // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ------------------------
-        float4 c1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0]);
-        float4 c2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0]);
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) {
-            float4 d1, d2;
-            if (r < RPT - 1) {
-                d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + (r + 1) * TW]);
-                d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + (r + 1) * TW]);
-            } else {
-                d1 = c1;  // region's last row: halo, or the mirrored image border
-                d2 = c2;
-                if (wq < kWarps - 1) {
-                    if (flagsync) wait_ge(&prog[wq + 1], base + 2 * it + 1, backoff);
-                    if (!(edge_y && rbot == RPT - 1)) {
-                        d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
-                        d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
-                    }
-                } else if (seam_bot) {  // first row of the CTA below, through distributed shared memory
-                    wait_ge_cluster(&sm_below->prog[0], base + 2 * it + 1);
-                    if (!(edge_y && rbot == RPT - 1)) {
-                        d1 = *reinterpret_cast<const float4 *>(&sm_below->u[0][4 * lane]);
-                        d2 = *reinterpret_cast<const float4 *>(&sm_below->u[1][4 * lane]);
-                    }
-                }
-            }
-            float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
-            float r2 = __shfl_down_sync(0xffffffffu, c2.x, 1);
-            if (edge_x && jlast == 3) {
-                r1 = c1.w;
-                r2 = c2.w;
-            }
-            tvl1_dual_px(c1.y - c1.x, d1.x - c1.x, c2.y - c2.x, d2.x - c2.x, taut, p11[r].x, p12[r].x, p21[r].x, p22[r].x);
-            tvl1_dual_px(c1.z - c1.y, d1.y - c1.y, c2.z - c2.y, d2.y - c2.y, taut, p11[r].y, p12[r].y, p21[r].y, p22[r].y);
-            tvl1_dual_px(c1.w - c1.z, d1.z - c1.z, c2.w - c2.z, d2.z - c2.z, taut, p11[r].z, p12[r].z, p21[r].z, p22[r].z);
-            tvl1_dual_px(r1 - c1.w, d1.w - c1.w, r2 - c2.w, d2.w - c2.w, taut, p11[r].w, p12[r].w, p21[r].w, p22[r].w);
-            c1 = d1;
-            c2 = d2;
-        }
-        st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
-        st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);
-        if (seam_bot) signal_cluster(&sm.prog[wq], base + 2 * it + 2); else signal(&prog[wq], base + 2 * it + 2);
-        if (!flagsync) __syncthreads();
-    }
+    const float err = (t.edge_x || t.edge_y) ? tile_iterations<true>(sm, t, c, kk, check, p11, p12, p21, p22)
+                                             : tile_iterations<false>(sm, t, c, kk, check, p11, p12, p21, p22);
     if (prof_on) {
-        const unsigned long long t = gtime();
-        sm.prof[6] += t - t0;
-        t0 = t;
+        const unsigned long long tt = gtime();
+        sm.prof[6] += tt - t0;
+        t0 = tt;
     }
     // -------- write the interior to the other buffer ---------------------------------------------
     {
@@ -493,7 +504,7 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const FusedLe
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int ry = RPT * wq + r, gy = gy0 + r;
-            if (lane_in && ry >= ry_lo && ry < ry_hi && gy < H) {
+            if (t.lane_in && ry >= t.ry_lo && ry < t.ry_hi && gy < H) {
                 const size_t o = (size_t)gy * P + gx0;
                 st4(d0 + o, *reinterpret_cast<const float4 *>(&sm.u[0][so0 + r * TW]));
                 st4(d1 + o, *reinterpret_cast<const float4 *>(&sm.u[1][so0 + r * TW]));
@@ -549,20 +560,13 @@ struct Prof {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant__ FusedBatch batch) {
+__global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const __grid_constant__ FusedBatch batch) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int G = batch.group;
     const int lane_id = blockIdx.x / G, bid = blockIdx.x - lane_id * G;
     const FusedJob &job = batch.job[lane_id];
-    // optional 2-CTA clusters (launch attribute): the two CTAs of a cluster are consecutive block indices of one lane
-    const int csize = batch.cluster, crank = csize > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
-    Smem *sm_above = nullptr, *sm_below = nullptr;
-    if (csize > 1) {
-        auto cl = cooperative_groups::this_cluster();
-        if (crank > 0) sm_above = cl.map_shared_rank(&sm, crank - 1);
-        if (crank < csize - 1) sm_below = cl.map_shared_rank(&sm, crank + 1);
-    }
+    const Tvl1Consts c = job.c;  // by value: the job is indexed dynamically in the parameter bank
     unsigned epoch = 0;
     unsigned *bar = job.sync;
     int cur = 0;
@@ -613,11 +617,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     const int kk = (remaining + nch - 1) / nch;
                     const bool chk = check && kk == remaining;
                     const int hx = (kk + 3) & ~3, hy = kk;
-                    const int ntx = tiles_along(L.w, TW, hx), nty = tiles_along(L.h, TH * csize, hy);
+                    const int ntx = tiles_along(L.w, TW, hx), nty = tiles_along(L.h, TH, hy);
                     const int ntiles = ntx * nty;
-                    for (int t = bid / csize; t < ntiles; t += G / csize) {
+                    for (int t = bid; t < ntiles; t += G) {
                         const int ty = t / ntx, tx = t - ty * ntx;
-                        const float e = process_tile(job, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on, crank, csize, sm_above, sm_below);
+                        const float e = process_tile(job, c, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on);
                         tile_base += 2 * kk + 2;
                         tma_parity ^= 1u;
                         if (chk) {
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tvl1_pair(const __grid_constant
                     prev_error = pp;
                 }
             }
-            if (bid == 0 && threadIdx.x == 0) job.ctl->iters[s * job.warps + wi] = n;
+            if (bid == 0 && threadIdx.x == 0) job.iters_log[s * job.warps + wi] = n;
             px_iters += (unsigned long long)n * (unsigned long long)(L.w * L.h);
         }
         if (s > 0) {
@@ -726,29 +730,28 @@ int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
         const int d = device >= 0 && device < 64 ? device : 0;
         if (!configured[d]) {
             DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int resident = 0;
+            DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_tvl1_pair, kThreads, sizeof(Smem)));
+            if (resident < kFusedCtasPerSm)
+                throw std::runtime_error("k_tvl1_pair: only " + std::to_string(resident) + " CTA(s) fit an SM, the launch geometry needs " +
+                                         std::to_string(kFusedCtasPerSm));
             configured[d] = true;
         }
     }
     static_assert(TW == kFusedTileW && TH == kFusedTileH, "tile geometry is shared with the host heuristics");
-    // all CTAs must be co-resident (1 CTA / SM): group * njobs <= SM count, enforced by the cooperative launch
+    // all CTAs must be co-resident: group * njobs <= SM count x kFusedCtasPerSm, enforced by the cooperative launch
     const int grid = batch.group * batch.njobs;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = sizeof(Smem);
     cfg.stream = s;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[1];
     int na = 0;
     attrs[na].id = cudaLaunchAttributeCooperative;
     attrs[na].val.cooperative = 1;
     ++na;
-    if (batch.cluster > 1) {
-        attrs[na].id = cudaLaunchAttributeClusterDimension;
-        attrs[na].val.clusterDim.x = batch.cluster;
-        attrs[na].val.clusterDim.y = 1;
-        attrs[na].val.clusterDim.z = 1;
-        ++na;
-    }
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair, batch));

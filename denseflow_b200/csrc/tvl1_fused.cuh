@@ -18,7 +18,6 @@ struct FusedLevel {
 // Written by the kernel into mapped host memory (no memcpy, no sync on the pair path).
 struct FusedHostCtl {
     double error;         // unfused engine: convergence sum read by the host state machine
-    int iters[16 * 16];   // executed inner iterations per (scale, warp) of the last pair
     unsigned long long px_iters_total;  // sum over pairs of (level pixels x executed iterations)
     unsigned long long px_chunks_total; // sum over pairs of (level pixels x tile visits): 64 B of state/constant traffic each
     // CTA-0 view of where the last pair's time went, in ns (globaltimer): [0] level start, [1] warps,
@@ -41,8 +40,13 @@ struct FusedJob {
     double *partials;
     unsigned *sync;
     FusedHostCtl *ctl;
+    int *iters_log;  // [16 * 16] executed inner iterations per (scale, warp) of THIS pair, index s * warps + w (mapped host memory)
     float *flow_xy;
     size_t flow_pitch_bytes;
+    // bound > 0: emit the two quantised uint8 planes instead of the float2 field (PairJob)
+    int bound;
+    uint8_t *qx, *qy;
+    size_t q_pitch;
 };
 
 // Several independent pairs ("lanes") per launch: lane i is solved by CTAs [i*group, (i+1)*group) with
@@ -53,7 +57,6 @@ constexpr int kFusedMapsPerLevel = 8;
 constexpr int kTensorMapBytes = 128;  // sizeof(CUtensorMap)
 struct FusedBatch {
     int njobs, group;
-    int cluster;  // CTAs per thread-block cluster (1, or 2: two CTAs stacked vertically share a 128 x 128 region via DSMEM)
     FusedJob job[kFusedMaxLanes];
 };
 
@@ -69,8 +72,14 @@ __host__ __device__ inline int fused_tiles_along(int n, int T, int h) {
 #define DFB_FUSED_RPT 4
 #endif
 constexpr int kFusedTileW = 128, kFusedTileH = DFB_FUSED_THREADS / 32 * DFB_FUSED_RPT;
+// CTAs of the persistent kernel resident per SM: 512-thread CTAs own the whole SM (192 KB tile); 256-thread CTAs
+// (128 x 32 tiles, 96 KB) run two to an SM, so one CTA's MUFU-bound dual half-steps and tile loads overlap the
+// other's FMA-bound primal half-steps (the warps of ONE tile are forced into lock-step by their neighbour dependencies)
+constexpr int kFusedCtasPerSm = DFB_FUSED_THREADS <= 256 ? 2 : 1;
+constexpr int kFusedDefaultK = kFusedTileH >= 64 ? 8 : 4;
 
 int fused_num_sms(int device);
+inline int fused_cta_slots(int device) { return fused_num_sms(device) * kFusedCtasPerSm; }
 // Encodes one 2-D fp32 tile descriptor (box 128 x 64, no swizzle, zero fill out of bounds) into out[128 bytes].
 // plane: base pointer, extent w x h (elements / rows), row pitch in elements.
 void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pitch);

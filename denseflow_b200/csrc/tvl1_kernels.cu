@@ -109,20 +109,17 @@ __global__ void __launch_bounds__(BX *BY)
             t22 = ld4(p22.p + i - p22.pitch);
         }
         float4 n1, n2;
-        tvl1_primal_px(ix.x, iy.x, g.x, rc.x, uo1.x, uo2.x, (a11.x - l11) + (a12.x - t12.x), (a21.x - l21) + (a22.x - t22.x), c, n1.x, n2.x);
-        tvl1_primal_px(ix.y, iy.y, g.y, rc.y, uo1.y, uo2.y, (a11.y - a11.x) + (a12.y - t12.y), (a21.y - a21.x) + (a22.y - t22.y), c, n1.y, n2.y);
-        tvl1_primal_px(ix.z, iy.z, g.z, rc.z, uo1.z, uo2.z, (a11.z - a11.y) + (a12.z - t12.z), (a21.z - a21.y) + (a22.z - t22.z), c, n1.z, n2.z);
-        tvl1_primal_px(ix.w, iy.w, g.w, rc.w, uo1.w, uo2.w, (a11.w - a11.z) + (a12.w - t12.w), (a21.w - a21.z) + (a22.w - t22.w), c, n1.w, n2.w);
+        const float4 gq = make_float4(tvl1_gq_from_grad(g.x), tvl1_gq_from_grad(g.y), tvl1_gq_from_grad(g.z), tvl1_gq_from_grad(g.w));
+        tvl1_primal_row(ix, iy, gq, rc, uo1, uo2, a11, l11, a12, t12, a21, l21, a22, t22, c, n1, n2);
         st4(u1.p + i, n1);
         st4(u2.p + i, n2);
         if (CALC_ERROR) {
             // diff = (u1-u1')^2 + (u2-u2')^2 in fp32 per pixel, accumulated in double (cuda::sum)
-            float d;
-            d = (uo1.x - n1.x) * (uo1.x - n1.x) + (uo2.x - n2.x) * (uo2.x - n2.x);
-            err += (double)d;
-            if (x0 + 1 < W) { d = (uo1.y - n1.y) * (uo1.y - n1.y) + (uo2.y - n2.y) * (uo2.y - n2.y); err += (double)d; }
-            if (x0 + 2 < W) { d = (uo1.z - n1.z) * (uo1.z - n1.z) + (uo2.z - n2.z) * (uo2.z - n2.z); err += (double)d; }
-            if (x0 + 3 < W) { d = (uo1.w - n1.w) * (uo1.w - n1.w) + (uo2.w - n2.w) * (uo2.w - n2.w); err += (double)d; }
+            const float4 d = tvl1_diff_row(uo1, uo2, n1, n2);
+            err += (double)d.x;
+            if (x0 + 1 < W) err += (double)d.y;
+            if (x0 + 2 < W) err += (double)d.z;
+            if (x0 + 3 < W) err += (double)d.w;
         }
     }
     if (CALC_ERROR) {
@@ -155,15 +152,13 @@ __global__ void __launch_bounds__(BX *BY)
     const int xr = min(x0 + 4, W - 1);
     const float r1 = u1.p[(size_t)y * u1.pitch + xr], r2 = u2.p[(size_t)y * u2.pitch + xr];
     float4 b11 = ld4(p11.p + i), b12 = ld4(p12.p + i), b21 = ld4(p21.p + i), b22 = ld4(p22.p + i);
-    // u(x+1) - u(x), with u(x+1) = u(x) when x == W-1
-    const float e1x = (x0 + 1 < W ? a1.y : a1.x) - a1.x, e2x = (x0 + 1 < W ? a2.y : a2.x) - a2.x;
-    const float f1x = (x0 + 2 < W ? a1.z : a1.y) - a1.y, f2x = (x0 + 2 < W ? a2.z : a2.y) - a2.y;
-    const float g1x = (x0 + 3 < W ? a1.w : a1.z) - a1.z, g2x = (x0 + 3 < W ? a2.w : a2.z) - a2.z;
-    const float h1x = (x0 + 4 < W ? r1 : a1.w) - a1.w, h2x = (x0 + 4 < W ? r2 : a2.w) - a2.w;
-    tvl1_dual_px(e1x, d1.x - a1.x, e2x, d2.x - a2.x, c.taut, b11.x, b12.x, b21.x, b22.x);
-    tvl1_dual_px(f1x, d1.y - a1.y, f2x, d2.y - a2.y, c.taut, b11.y, b12.y, b21.y, b22.y);
-    tvl1_dual_px(g1x, d1.z - a1.z, g2x, d2.z - a2.z, c.taut, b11.z, b12.z, b21.z, b22.z);
-    tvl1_dual_px(h1x, d1.w - a1.w, h2x, d2.w - a2.w, c.taut, b11.w, b12.w, b21.w, b22.w);
+    // u(x+1) - u(x) with u(x+1) = u(x) when x == W-1: mirror the last image column into the pixels right of it (their own
+    // results land in the padding columns and are never read as image data)
+    float4 c1 = a1, c2 = a2;
+    if (x0 + 1 >= W) { c1.y = c1.x; c2.y = c2.x; }
+    if (x0 + 2 >= W) { c1.z = c1.y; c2.z = c2.y; }
+    if (x0 + 3 >= W) { c1.w = c1.z; c2.w = c2.z; }
+    tvl1_dual_row(c1, c2, d1, d2, x0 + 4 < W ? r1 : c1.w, x0 + 4 < W ? r2 : c2.w, c.taut, b11, b12, b21, b22);
     st4(p11.p + i, b11);
     st4(p12.p + i, b12);
     st4(p21.p + i, b21);
@@ -202,16 +197,7 @@ __global__ void k_merge_flow(Plane u1, Plane u2, float *flow, size_t flow_pitch_
     row[x] = make_float2(u1.p[(size_t)y * u1.pitch + x], u2.p[(size_t)y * u2.pitch + x]);
 }
 
-// convertFlowToImage, /root/reference/src/common.cpp:4-16: the CAST macro evaluates in double
-// (bounds are double), left to right, then cvRound (round-half-to-even).
-__device__ __forceinline__ uint8_t quantise_px(float v, double L, double H) {
-    if ((double)v > H) return 255;
-    if ((double)v < L) return 0;
-    const double q = 255 * ((double)v - L) / (H - L);
-    if (q != q) return 0;
-    return (uint8_t)__double2int_rn(q);
-}
-
+// convertFlowToImage, /root/reference/src/common.cpp:4-16 (quantise_px, common.cuh)
 __global__ void k_quantise(const float *flow, size_t flow_pitch_bytes, int w, int h, double L, double H, uint8_t *qx,
                            uint8_t *qy, size_t q_pitch) {
     const int x = blockIdx.x * BX + threadIdx.x;

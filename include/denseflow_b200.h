@@ -60,10 +60,9 @@ const char *dfb_last_error(const dfb_handle *h);
  * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations"
  * "scale_step"; engine knobs: "fused" (1 = persistent fused primal+dual kernel [default], 0 = one
  * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile),
- * "lanes" (pairs solved side by side per launch, 0 = auto, up to 16), "flag_sync" (1 = neighbour-warp progress flags
+ * "lanes" (pairs solved side by side per launch, 0 = auto, up to 16); "scale_step" must not exceed the default 0.8 the workspace is sized for, "flag_sync" (1 = neighbour-warp progress flags
  * in the tile loop [default], 0 = CTA-wide barriers), "use_tma" (1 = TMA staging of the shared-memory tiles [default]),
- * "cluster" (2 = experimental 2-CTA thread-block clusters, default 1), "time_kernels" (CUDA-event timing of the fused
- * kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma" (winSize 13, polyN 5, pyrScale 0.5 are fixed).
+ * "time_kernels" (CUDA-event timing of the fused kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma" (winSize 13, polyN 5, pyrScale 0.5 are fixed).
  * Every combination of the engine knobs produces bit-identical flows.
  */
 int dfb_set_param(dfb_handle *h, const char *name, double value);
@@ -148,6 +147,10 @@ typedef struct {
     int iters[16 * 16];
 } dfb_tvl1_stats;
 int dfb_get_tvl1_stats(dfb_handle *h, dfb_tvl1_stats *out);
+/* The same log for pair `pair_index` (0-based, in output order) of the most recent calc / batch call on this handle;
+ * the engine keeps the last 256 pairs of a call.  Lets a test compare the executed schedule of every pair of a batch
+ * with the oracle's. */
+int dfb_get_tvl1_pair_stats(dfb_handle *h, int pair_index, dfb_tvl1_stats *out);
 
 /*
  * The reference's per-batch chain minus decode and file IO, on the GPU, for decoded BGR frames:
@@ -206,6 +209,50 @@ int dfb_get_counters(dfb_handle *h, dfb_counters *out);
  */
 int dfb_get_tvl1_phase_ns(dfb_handle *h, uint64_t out[32]);
 int dfb_reset_counters(dfb_handle *h);
+
+/*
+ * ---- video-list dispatch over several GPUs (SURVEY §8 e; BASELINE.json configs[4]) --------------------------------
+ * The reference builds the list of videos from list.txt (tools/denseflow.cpp:54-81) and walks it on GPU 0
+ * (src/denseflow_gpu.cpp:482-489); a video is marked done only after its last FlowBuffer has been written (:456-470).
+ * dfb_run_list drains the same kind of list with n_workers host threads (worker i owns an engine handle on
+ * devices[i]; a device may appear twice so one worker's copies overlap the other's compute) from ONE dynamic work
+ * queue — no static i mod G assignment, no data-path collective, unit of work = one video.
+ *   queue == NULL : in-process atomic counter (one process, one thread per GPU — the reference's process model)
+ *   queue != NULL : a counter in POSIX shared memory shared by several processes (one process per GPU, e.g. torchrun):
+ *                   every process passes the SAME clip list and its own device; each index is handed out exactly once.
+ * Each video is solved in chunks of at most chunk_flows flows (0 = 64), frames overlapping by |step| between chunks as
+ * the reference's own batches do (:182-189), and reported through `done` on the worker's thread once every output of
+ * the chunk is in host memory:
+ *   first_flow      global index of the chunk's first flow inside the video (FlowBuffer::base_start)
+ *   last_chunk      1 for the final chunk of the video (FlowBuffer::last_buffer): the only point at which the host may
+ *                   create the video's .done marker
+ *   qx/qy           bound > 0: the convertFlowToImage planes (width*height uint8 each), flows == NULL
+ *   flows           bound == 0: CV_32FC2 fields, qx == qy == NULL
+ * The buffers belong to the worker and are reused after the callback returns.
+ */
+typedef struct dfb_queue dfb_queue;
+int dfb_queue_open(const char *name, int create, dfb_queue **out); /* name: "/something" (shm_open); create = 1 also zeroes it */
+long dfb_queue_next(dfb_queue *q);                                  /* atomic fetch-and-increment */
+void dfb_queue_reset(dfb_queue *q);
+void dfb_queue_close(dfb_queue *q, int unlink_name);
+
+typedef struct {
+    const uint8_t *const *frames; /* n_frames host pointers to dense width*height gray frames (pinned or pageable) */
+    int n_frames, width, height;
+} dfb_clip;
+typedef void (*dfb_chunk_done_fn)(void *user, int clip_index, int device, int first_flow, int n_flows, int last_chunk,
+                                  uint8_t *const *qx, uint8_t *const *qy, float *const *flows);
+#define DFB_LIST_MAX_WORKERS 32
+typedef struct {
+    uint64_t clips, flows, frames; /* processed by THIS call (this process) */
+    double seconds;                /* wall time of the call */
+    int workers;
+    uint64_t clips_per_worker[DFB_LIST_MAX_WORKERS], flows_per_worker[DFB_LIST_MAX_WORKERS];
+    double busy_seconds_per_worker[DFB_LIST_MAX_WORKERS];   /* time spent inside clips */
+    double finish_seconds_per_worker[DFB_LIST_MAX_WORKERS]; /* when the worker ran out of work (tail imbalance) */
+} dfb_list_stats;
+int dfb_run_list(const char *algorithm, const int *devices, int n_workers, const dfb_clip *clips, int n_clips, int step, int bound,
+                 int chunk_flows, dfb_queue *queue, dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len);
 
 #ifdef __cplusplus
 }

@@ -7,10 +7,11 @@ from denseflow_b200 import synth
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
 ks = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [8]
 lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+variant = sys.argv[5] if len(sys.argv) > 5 else "default"
 fr = synth.stream(H, W, 4, seed=1)
 dev = torch.from_numpy(fr).cuda()
 for k in ks:
-    e = d.OpticalFlowDual_TVL1.create(0, W, H)
+    e = d.OpticalFlowDual_TVL1.create(0, W, H, variant)
     e.set("fused_k", k); e.set("lanes", lanes)
     out = e.calc_batch_device(dev, 1); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

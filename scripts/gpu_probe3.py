@@ -12,10 +12,12 @@ dev = torch.from_numpy(fr).cuda()
 out = torch.empty((N - 1, H, W, 2), dtype=torch.float32, device="cuda")
 ref = None
 variants = sys.argv[3].split(',') if len(sys.argv) > 3 else ['default']
-cfgs = [(v, l, k, t) for v in variants for (l, k, t) in [(1, 8, 1), (0, 8, 1), (4, 8, 1), (0, 6, 1)]]
+ks = [int(x) for x in sys.argv[5].split(',')] if len(sys.argv) > 5 else [8]
+lane_list = [int(x) for x in sys.argv[6].split(',')] if len(sys.argv) > 6 else [1, 0]
+cfgs = [(v, l, k, 1) for v in variants for k in ks for l in lane_list]
 for variant, lanes, k, fs in cfgs:
     e = d.OpticalFlowDual_TVL1.create(0, W, H, variant)
-    e.set("lanes", lanes); e.set("fused_k", k); e.set("cluster", fs)
+    e.set("lanes", lanes); e.set("fused_k", k)
     e.calc_batch_device(dev, 1, out); torch.cuda.synchronize()
     e.reset_counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,6 +26,6 @@ for variant, lanes, k, fs in cfgs:
     c = e.counters()
     res = out.cpu().numpy()
     if ref is None: ref = res.copy()
-    print("%s cluster=%d " % (variant, fs), end=""); print("lanes=%d k=%d: %.3f ms/pair (%.1f pairs/s), launches %d, px-iters/pair %.1fM, max|diff| vs lanes=1: %.2e" % (
+    print("%s " % variant, end=""); print("lanes=%d k=%d: %.3f ms/pair (%.1f pairs/s), launches %d, px-iters/pair %.1fM, max|diff| vs lanes=1: %.2e" % (
         lanes, k, dt / (N - 1) * 1e3, (N - 1) / dt, c["kernel_launches"], c["pixel_iters"] / (N - 1) / 1e6, np.abs(res - ref).max()))
     e.release()
