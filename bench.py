@@ -67,6 +67,12 @@ def parse():
     ap.add_argument("--pairs", type=int, default=16, help="frame pairs per step")
     ap.add_argument("--cpu-sample-pairs", type=int, default=3, help="pairs timed for cpu_baseline (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # BASELINE.json configs[4]: a fixed list of clips dispatched over the GPUs from one dynamic queue (strong scaling)
+    ap.add_argument("--list", type=int, default=0, help="list mode: number of clips in the video list (e.g. 1024); a step = one pass over the list")
+    ap.add_argument("--list-frames", type=int, default=64, help="frames per clip")
+    ap.add_argument("--list-distinct", type=int, default=8, help="distinct synthetic clips the list cycles through")
+    ap.add_argument("--list-bound", type=int, default=32, help="-b of the CLI (default 32): the uint8 planes come back")
+    ap.add_argument("--workers-per-gpu", type=int, default=2, help="list mode: host threads (engine handles) per GPU")
     return ap.parse_args()
 
 
@@ -242,11 +248,125 @@ def run_reference(args, alg, W, H, seed, desc):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def run_list_mode(args, alg, W, H, seed, desc):
+    """--list N: a FIXED list of N clips (BASELINE.json configs[4]: 1024 x 340x256x64) drained from one dynamic work queue
+    by all GPUs of the job: one process per GPU under torchrun (queue in POSIX shared memory), or one process with
+    --gpus x --workers-per-gpu threads.  Unit of work = one video; host frames in, the convertFlowToImage planes back in
+    host memory (what the jpg writer consumes); strong scaling; time = max over ranks of the wall time of the pass."""
+    import numpy as np
+    import torch
+    import denseflow_b200 as d
+    from denseflow_b200 import listrun, shard, synth
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    rank, local_rank, world = shard.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wpg = max(1, args.workers_per_gpu)
+    if world > 1:
+        mode, n_gpus, devices = "one process per GPU, %d worker threads each, queue in POSIX shared memory" % wpg, world, [local_rank] * wpg
+    else:
+        mode, n_gpus = "one process, %d worker threads per GPU, in-process queue" % wpg, max(1, args.gpus)
+        devices = [g for g in range(n_gpus) for _ in range(wpg)]
+    N, F, NB, bound = args.list, args.list_frames, max(1, min(args.list_distinct, args.list)), args.list_bound
+    base = [torch.from_numpy(synth.stream(H, W, F, seed + c, phase=float(c))).pin_memory() for c in range(NB)]
+    base_np = [b.numpy() for b in base]
+    clips = [[base_np[i % NB][t] for t in range(F)] for i in range(N)]
+    runner = listrun.ListRunner(alg, devices, W, H)
+    packed = runner.pack(clips)
+    warm = runner.pack(clips[:2 * len(devices)])
+    queue = None
+    if world > 1:
+        qname = "/dfb_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            queue = listrun.WorkQueue(qname, create=True)
+        shard.barrier()
+        if rank != 0:
+            queue = listrun.WorkQueue(qname, create=False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 1)):  # private queue: every worker of every rank gets warm (lanes, pinned rings, clocks)
+        runner.run(None, step=1, bound=bound, packed=warm)
+    torch.cuda.synchronize(dev)
+    tot = {"flows": 0, "clips": 0, "launches": 0, "h2d": 0, "d2h": 0}
+    dts, last = [], None
+    tmark0 = sampler.mark()
+    for _ in range(args.steps):
+        shard.barrier()
+        if queue is not None and rank == 0:
+            queue.reset()
+        shard.barrier()
+        t0 = time.perf_counter()
+        last = runner.run(None, step=1, bound=bound, queue=queue, packed=packed)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        dts.append(shard.all_max(dt, dev))
+        for k, key in (("flows", "flows"), ("clips", "clips"), ("launches", "kernel_launches"), ("h2d", "h2d_bytes"), ("d2h", "d2h_bytes")):
+            tot[k] += last[key]
+    tmark1 = sampler.mark()
+    g = {k: shard.all_sum(v, dev) for k, v in tot.items()}
+    per_rank_clips = [int(shard.all_sum(last["clips"] if r == rank else 0, dev)) for r in range(world)]
+    finish = last["finish_seconds_per_worker"]
+    tail = shard.all_max(max(finish), dev) - (-shard.all_max(-min(finish), dev))
+    busy = shard.all_sum(sum(last["busy_seconds_per_worker"]), dev) / (max(dts[-1], 1e-9) * len(devices) * world)
+    clocks = sampler.stop(tmark0, tmark1) if rank == 0 else None
+    parity = None
+    if rank == 0:
+        from oracle import pyoracle as O
+        e = d.create(alg, local_rank, W, H)
+        a, b = base_np[0][0], base_np[0][1]
+        got = e.calc_batch([a, b], 1)[0]
+        qx, qy = e.calc_batch([a, b], 1, bound=bound)
+        ref = (O.tvl1_calc if alg == "tvl1" else O.farn_calc)(a, b)
+        ox, oy = O.quantise(ref, bound)
+        parity = {"aee_px": synth.aee(got, ref), "pair": "clip 0, frames 0-1",
+                  "quantised_planes_equal_fraction": float(((qx[0] == ox) & (qy[0] == oy)).mean()),
+                  "quantised_max_level_diff": int(max(np.abs(qx[0].astype(int) - ox).max(), np.abs(qy[0].astype(int) - oy).max())),
+                  "against": "oracle (CPU restatement)", "tolerance_px": 0.01}
+        e.release()
+    if rank == 0:
+        total_s = sum(dts)
+        value = g["flows"] / total_s
+        line = {
+            "metric": "%s flow-pairs/sec at %dx%d, %d-clip list" % (alg, W, H, N), "value": value, "unit": "pairs/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "algorithm": alg, "width": W, "height": H, "step": 1, "list_clips": N, "frames_per_clip": F,
+                       "distinct_clips": NB, "bound": bound, "mode": mode, "queue": "dynamic (fetch-and-increment), unit = one video",
+                       "completion": "a video is reported done after its last chunk's planes are in host memory (src/denseflow_gpu.cpp:456-470)",
+                       "value_is": "end to end (there is no HBM-resident variant of a list job): pinned host frames in, uint8 planes out",
+                       "l2": "each clip's frames and outputs are touched once; 16 lanes x ~20 MB of planes per launch"},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": g["h2d"] / args.steps, "d2h_bytes_per_step": g["d2h"] / args.steps,
+                    "call": "dfb_list_run -> dfb_calc_batch_host_u8 per video"},
+            "gpu_launches": int(g["launches"]), "clocks": clocks,
+            "list": {"clips_per_rank_last_step": per_rank_clips, "clips_per_worker_rank0": last["clips_per_worker"],
+                     "tail_seconds_last_step": tail, "worker_busy_fraction_last_step": busy, "seconds_per_step": dts},
+        }
+        if parity:
+            line["parity_aee_px"] = parity["aee_px"]
+            line["parity"] = parity
+        print(json.dumps(line), flush=True)
+    runner.close()
+    if queue is not None:
+        shard.barrier()
+        queue.close()
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     args = parse()
     alg, W, H, seed, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, alg, W, H, seed, desc)
+    if args.list > 0:
+        return run_list_mode(args, alg, W, H, seed, desc)
 
     import numpy as np
     import torch

@@ -45,7 +45,8 @@ class Clip(C.Structure):
 class ListStats(C.Structure):
     _fields_ = [("clips", C.c_uint64), ("flows", C.c_uint64), ("frames", C.c_uint64), ("seconds", C.c_double), ("workers", C.c_int),
                 ("clips_per_worker", C.c_uint64 * LIST_MAX_WORKERS), ("flows_per_worker", C.c_uint64 * LIST_MAX_WORKERS),
-                ("busy_seconds_per_worker", C.c_double * LIST_MAX_WORKERS), ("finish_seconds_per_worker", C.c_double * LIST_MAX_WORKERS)]
+                ("busy_seconds_per_worker", C.c_double * LIST_MAX_WORKERS), ("finish_seconds_per_worker", C.c_double * LIST_MAX_WORKERS),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 CHUNK_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -71,6 +72,8 @@ SIGNATURES = {
                                         C.c_void_p]),
     "dfb_quantise_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dfb_flow_to_png_image_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_double), C.c_void_p]),
     "dfb_bgr_to_gray_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dfb_resize_gray_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int,
                                          C.c_int, C.c_void_p]),
@@ -92,6 +95,10 @@ SIGNATURES = {
     "dfb_queue_next": (C.c_long, [C.c_void_p]),
     "dfb_queue_reset": (None, [C.c_void_p]),
     "dfb_queue_close": (None, [C.c_void_p, C.c_int]),
+    "dfb_list_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
+    "dfb_list_run": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.POINTER(ListStats), C.c_char_p, C.c_size_t]),
+    "dfb_list_close": (None, [C.c_void_p]),
     "dfb_run_list": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(Clip), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.POINTER(ListStats), C.c_char_p, C.c_size_t]),
 }

@@ -159,6 +159,18 @@ class DenseOpticalFlow:
                                                 qx.data_ptr(), qy.data_ptr(), w, C.c_void_p(s)))
         return qx, qy
 
+    # -- convertFlowToPngImage (src/common.cpp:18-46): the CV_8UC3 image `-st=png` encodes --
+    def flow_to_png_image_device(self, flow, return_bounds=True):
+        """flow: CUDA float32 [H,W,2].  Returns (bgr uint8 [H,W,3] CUDA tensor, (bound_x, bound_y) or None)."""
+        import torch
+        h, w = flow.shape[:2]
+        bgr = torch.empty((h, w, 3), dtype=torch.uint8, device=flow.device)
+        b = (C.c_double * 2)()
+        s = torch.cuda.current_stream(flow.device).cuda_stream
+        self._check(self._L.dfb_flow_to_png_image_device(self._h, flow.data_ptr(), flow.stride(0) * 4, w, h, bgr.data_ptr(), w * 3,
+                                                         b if return_bounds else None, C.c_void_p(s)))
+        return bgr, ((b[0], b[1]) if return_bounds else None)
+
     # -- frame preparation (cvtColor BGR2GRAY + resize INTER_LINEAR, src/denseflow_gpu.cpp:163-170), bit-exact to OpenCV CPU --
     def bgr_to_gray_device(self, bgr):
         import torch

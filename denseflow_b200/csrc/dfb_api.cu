@@ -11,6 +11,7 @@
 
 #include "engine.h"
 #include "jpeg.h"
+#include "png_pack.h"
 #include "preproc.h"
 #include "tvl1.cuh"
 
@@ -43,6 +44,7 @@ struct dfb_handle {
     uint8_t *pb_bgr = nullptr, *pb_gray = nullptr, *pb_frames = nullptr, *pb_q = nullptr;
     float *pb_flows = nullptr;
     size_t pb_bgr_cap = 0, pb_gray_cap = 0, pb_frames_cap = 0, pb_q_cap = 0, pb_flows_cap = 0;
+    void *png_scratch = nullptr;  // min/max partials + ticket + bounds of dfb_flow_to_png_image_device
     ResizeTap *d_taps = nullptr;
     int taps_cap = 0, taps_sw = 0, taps_sh = 0, taps_dw = 0, taps_dh = 0;
 };
@@ -336,6 +338,7 @@ void dfb_destroy(dfb_handle *h) {
     for (void *p : {(void *)h->pb_bgr, (void *)h->pb_gray, (void *)h->pb_frames, (void *)h->pb_q, (void *)h->pb_flows})
         if (p) cudaFree(p);
     if (h->d_taps) cudaFree(h->d_taps);
+    if (h->png_scratch) cudaFree(h->png_scratch);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -469,6 +472,36 @@ int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, 
         DFB_CUDA(cudaSetDevice(h->device));
         launch_quantise(flow_xy, flow_pitch, width, height, bound, qx, qy, q_pitch, static_cast<cudaStream_t>(stream));
         ++h->alg->launches;
+        return DFB_OK;
+    });
+}
+
+int dfb_flow_to_png_image_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, int width, int height, uint8_t *bgr,
+                                  size_t bgr_pitch, double *bounds_xy_host, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!flow_xy || !bgr) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    if (width <= 0 || height <= 0 || flow_pitch < (size_t)width * 8 || bgr_pitch < (size_t)width * 3)
+        return fail(h, DFB_ERR_INVALID_ARG, "bad geometry");
+    if ((reinterpret_cast<uintptr_t>(flow_xy) | flow_pitch) & 7)
+        return fail(h, DFB_ERR_INVALID_ARG, "flow_xy and flow_pitch must be 8-byte aligned (CV_32FC2 rows)");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (!h->png_scratch) {
+            DFB_CUDA(cudaMalloc(&h->png_scratch, png_pack_scratch_bytes()));
+            DFB_CUDA(cudaMemset(h->png_scratch, 0, png_pack_scratch_bytes()));
+            DFB_CUDA(cudaDeviceSynchronize());
+        }
+        PngBounds *bd = nullptr;
+        launch_flow_to_png_image(flow_xy, flow_pitch, width, height, bgr, bgr_pitch, h->png_scratch, &bd, s);
+        h->alg->launches += 2;
+        if (bounds_xy_host) {  // the caller wants the two bounds now: a blocking read-back of 16 bytes
+            PngBounds b{};
+            DFB_CUDA(cudaMemcpyAsync(&b, bd, sizeof(b), cudaMemcpyDeviceToHost, s));
+            DFB_CUDA(cudaStreamSynchronize(s));
+            bounds_xy_host[0] = b.bound_x;
+            bounds_xy_host[1] = b.bound_y;
+        }
         return DFB_OK;
     });
 }

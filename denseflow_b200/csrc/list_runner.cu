@@ -80,59 +80,112 @@ void dfb_queue_close(dfb_queue *q, int unlink_name) {
     delete q;
 }
 
-int dfb_run_list(const char *algorithm, const int *devices, int n_workers, const dfb_clip *clips, int n_clips, int step, int bound,
-                 int chunk_flows, dfb_queue *queue, dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len) {
+struct dfb_list_runner {
+    std::string algorithm;
+    int max_w = 0, max_h = 0;
+    struct Worker {
+        int device = 0;
+        dfb_handle *h = nullptr;
+        void *pinned = nullptr;  // output ring of one chunk: the copy engines write the results straight into it
+        size_t pinned_bytes = 0;
+    };
+    std::vector<Worker> workers;
+};
+
+int dfb_list_open(const char *algorithm, const int *devices, int n_workers, int max_width, int max_height, dfb_list_runner **out, char *err,
+                  size_t err_len) {
     auto set_err = [&](const std::string &m) {
         if (err && err_len) std::snprintf(err, err_len, "%s", m.c_str());
     };
-    if (!algorithm || !devices || n_workers < 1 || n_workers > DFB_LIST_MAX_WORKERS || (!clips && n_clips > 0) || n_clips < 0 || step == 0 ||
-        bound < 0) {
-        set_err("dfb_run_list: bad arguments (step must be non-zero: step 0 is the frame-extraction mode)");
+    if (!out) return DFB_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!algorithm || !devices || n_workers < 1 || n_workers > DFB_LIST_MAX_WORKERS || max_width <= 0 || max_height <= 0) {
+        set_err("dfb_list_open: bad arguments");
+        return DFB_ERR_INVALID_ARG;
+    }
+    dfb_list_runner *r = new dfb_list_runner();
+    r->algorithm = algorithm;
+    r->max_w = max_width;
+    r->max_h = max_height;
+    for (int wi = 0; wi < n_workers; ++wi) {
+        dfb_list_runner::Worker w;
+        w.device = devices[wi];
+        if (int rc = dfb_create(algorithm, w.device, max_width, max_height, &w.h)) {
+            set_err("worker " + std::to_string(wi) + ": " + dfb_last_error(nullptr));
+            dfb_list_close(r);
+            return rc;
+        }
+        r->workers.push_back(w);
+    }
+    *out = r;
+    return DFB_OK;
+}
+
+void dfb_list_close(dfb_list_runner *r) {
+    if (!r) return;
+    for (auto &w : r->workers) {
+        cudaSetDevice(w.device);
+        if (w.pinned) cudaFreeHost(w.pinned);
+        dfb_destroy(w.h);
+    }
+    delete r;
+}
+
+int dfb_list_run(dfb_list_runner *r, const dfb_clip *clips, int n_clips, int step, int bound, int chunk_flows, dfb_queue *queue,
+                 dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len) {
+    auto set_err = [&](const std::string &m) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", m.c_str());
+    };
+    if (!r || (!clips && n_clips > 0) || n_clips < 0 || step == 0 || bound < 0) {
+        set_err("dfb_list_run: bad arguments (step must be non-zero: step 0 is the frame-extraction mode)");
         return DFB_ERR_INVALID_ARG;
     }
     if (chunk_flows <= 0) chunk_flows = 64;
     const int astep = std::abs(step);
-    int max_w = 1, max_h = 1;
+    const int n_workers = (int)r->workers.size();
     for (int i = 0; i < n_clips; ++i) {
         if (clips[i].n_frames < 0 || clips[i].width <= 0 || clips[i].height <= 0 || (clips[i].n_frames > 0 && !clips[i].frames)) {
-            set_err("dfb_run_list: clip " + std::to_string(i) + " is malformed");
+            set_err("dfb_list_run: clip " + std::to_string(i) + " is malformed");
             return DFB_ERR_INVALID_ARG;
         }
-        max_w = std::max(max_w, clips[i].width);
-        max_h = std::max(max_h, clips[i].height);
+        if (clips[i].width > r->max_w || clips[i].height > r->max_h) {
+            set_err("dfb_list_run: clip " + std::to_string(i) + " exceeds the size given to dfb_list_open");
+            return DFB_ERR_SIZE;
+        }
     }
     dfb_list_stats st{};
+    st.workers = n_workers;
     std::atomic<long> local_next{0};
     std::atomic<int> failed{0};
-    std::mutex err_mutex;
+    std::mutex mtx;
     std::string first_error;
     auto fail = [&](int code, const std::string &m) {
-        std::lock_guard<std::mutex> lk(err_mutex);
+        std::lock_guard<std::mutex> lk(mtx);
         if (!failed.load()) {
             failed.store(code);
             first_error = m;
         }
     };
-    const size_t px_max = (size_t)max_w * max_h;
+    const size_t px_max = (size_t)r->max_w * r->max_h;
+    const size_t out_bytes = (size_t)chunk_flows * px_max * (bound > 0 ? 2 : 8);
+    for (auto &w : r->workers) dfb_reset_counters(w.h);
     const auto t_start = clk::now();
 
     auto worker = [&](int wi) {
-        const int dev = devices[wi];
-        dfb_handle *h = nullptr;
-        if (int rc = dfb_create(algorithm, dev, max_w, max_h, &h)) {
-            fail(rc, std::string("worker ") + std::to_string(wi) + ": " + dfb_last_error(nullptr));
-            return;
+        dfb_list_runner::Worker &w = r->workers[wi];
+        cudaSetDevice(w.device);
+        if (w.pinned_bytes < out_bytes) {
+            if (w.pinned) cudaFreeHost(w.pinned);
+            w.pinned = nullptr;
+            w.pinned_bytes = 0;
+            if (cudaHostAlloc(&w.pinned, out_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                fail(DFB_ERR_CUDA, "worker " + std::to_string(wi) + ": pinned output allocation failed");
+                return;
+            }
+            w.pinned_bytes = out_bytes;
         }
-        // pinned output ring of one chunk: the copy engines write the results straight into it
-        uint8_t *qbuf = nullptr;
-        float *fbuf = nullptr;
-        cudaSetDevice(dev);
-        const size_t out_bytes = (size_t)chunk_flows * px_max * (bound > 0 ? 2 : 8);
-        if (cudaHostAlloc(bound > 0 ? (void **)&qbuf : (void **)&fbuf, out_bytes, cudaHostAllocDefault) != cudaSuccess) {
-            fail(DFB_ERR_CUDA, "worker " + std::to_string(wi) + ": pinned output allocation failed");
-            dfb_destroy(h);
-            return;
-        }
+        uint8_t *qbuf = bound > 0 ? static_cast<uint8_t *>(w.pinned) : nullptr;
+        float *fbuf = bound > 0 ? nullptr : static_cast<float *>(w.pinned);
         std::vector<uint8_t *> qx(chunk_flows), qy(chunk_flows);
         std::vector<float *> fl(chunk_flows);
         double busy = 0;
@@ -151,57 +204,87 @@ int dfb_run_list(const char *algorithm, const int *devices, int n_workers, const
             // chunks of flows [f0, f0 + m): frames f0 .. f0 + m - 1 + |step| (the overlap the reference keeps between its
             // own <= 512-frame batches, src/denseflow_gpu.cpp:182-189,204-205), so flow indices stay global (base_start)
             int f0 = 0;
-            do {
-                const int m = std::min(chunk_flows, M - f0);
+            for (;;) {
+                const int m = std::max(std::min(chunk_flows, M - f0), 0);
                 int rc = DFB_OK;
-                if (m > 0) {
-                    rc = bound > 0 ? dfb_calc_batch_host_u8(h, c.frames + f0, m + astep, step, c.width, c.height, bound, qx.data(), qy.data())
-                                   : dfb_calc_batch_host(h, c.frames + f0, m + astep, step, c.width, c.height, fl.data());
-                }
+                if (m > 0)
+                    rc = bound > 0 ? dfb_calc_batch_host_u8(w.h, c.frames + f0, m + astep, step, c.width, c.height, bound, qx.data(), qy.data())
+                                   : dfb_calc_batch_host(w.h, c.frames + f0, m + astep, step, c.width, c.height, fl.data());
                 if (rc != DFB_OK) {
-                    fail(rc, "clip " + std::to_string(idx) + ": " + dfb_last_error(h));
+                    fail(rc, "clip " + std::to_string(idx) + ": " + dfb_last_error(w.h));
                     break;
                 }
                 const int last = f0 + m >= M;
                 // every output of this chunk is in host memory now; `last` is the reference's FlowBuffer::last_buffer,
                 // the only point at which a video may be marked done
-                if (done) done(user, (int)idx, dev, f0, std::max(m, 0), last, bound > 0 ? qx.data() : nullptr, bound > 0 ? qy.data() : nullptr,
+                if (done) done(user, (int)idx, w.device, f0, m, last, bound > 0 ? qx.data() : nullptr, bound > 0 ? qy.data() : nullptr,
                                bound > 0 ? nullptr : fl.data());
-                f0 += std::max(m, 0);
+                f0 += m;
                 if (last) break;
-            } while (true);
+            }
             if (failed.load()) break;
             busy += seconds_since(t0);
-            {
-                std::lock_guard<std::mutex> lk(err_mutex);
-                ++st.clips;
-                st.flows += (uint64_t)M;
-                st.frames += (uint64_t)c.n_frames;
-                ++st.clips_per_worker[wi];
-                st.flows_per_worker[wi] += (uint64_t)M;
-            }
+            std::lock_guard<std::mutex> lk(mtx);
+            ++st.clips;
+            st.flows += (uint64_t)M;
+            st.frames += (uint64_t)c.n_frames;
+            ++st.clips_per_worker[wi];
+            st.flows_per_worker[wi] += (uint64_t)M;
         }
-        {
-            std::lock_guard<std::mutex> lk(err_mutex);
-            st.busy_seconds_per_worker[wi] = busy;
-            st.finish_seconds_per_worker[wi] = seconds_since(t_start);
-        }
-        cudaFreeHost(qbuf ? (void *)qbuf : (void *)fbuf);
-        dfb_destroy(h);
+        std::lock_guard<std::mutex> lk(mtx);
+        st.busy_seconds_per_worker[wi] = busy;
+        st.finish_seconds_per_worker[wi] = seconds_since(t_start);
     };
 
-    std::vector<std::thread> threads;
-    for (int wi = 1; wi < n_workers; ++wi) threads.emplace_back(worker, wi);
-    worker(0);
-    for (auto &t : threads) t.join();
+    if (n_clips > 0) {
+        std::vector<std::thread> threads;
+        for (int wi = 1; wi < n_workers; ++wi) threads.emplace_back(worker, wi);
+        worker(0);
+        for (auto &t : threads) t.join();
+    }
     st.seconds = seconds_since(t_start);
-    st.workers = n_workers;
+    for (auto &w : r->workers) {
+        dfb_counters c{};
+        if (dfb_get_counters(w.h, &c) == DFB_OK) {
+            st.kernel_launches += c.kernel_launches;
+            st.h2d_bytes += c.h2d_bytes;
+            st.d2h_bytes += c.d2h_bytes;
+        }
+    }
     if (stats) *stats = st;
     if (failed.load()) {
         set_err(first_error);
         return failed.load();
     }
     return DFB_OK;
+}
+
+int dfb_run_list(const char *algorithm, const int *devices, int n_workers, const dfb_clip *clips, int n_clips, int step, int bound,
+                 int chunk_flows, dfb_queue *queue, dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len) {
+    auto set_err = [&](const std::string &m) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", m.c_str());
+    };
+    if (!algorithm || !devices || n_workers < 1 || n_workers > DFB_LIST_MAX_WORKERS || (!clips && n_clips > 0) || n_clips < 0 || step == 0 ||
+        bound < 0) {
+        set_err("dfb_run_list: bad arguments (step must be non-zero: step 0 is the frame-extraction mode)");
+        return DFB_ERR_INVALID_ARG;
+    }
+    if (n_clips == 0) {  // tools/denseflow.cpp:86: nothing is created when every video of the list is already done
+        dfb_list_stats st{};
+        st.workers = n_workers;
+        if (stats) *stats = st;
+        return DFB_OK;
+    }
+    int max_w = 1, max_h = 1;
+    for (int i = 0; i < n_clips; ++i) {
+        max_w = std::max(max_w, clips[i].width);
+        max_h = std::max(max_h, clips[i].height);
+    }
+    dfb_list_runner *r = nullptr;
+    if (int rc = dfb_list_open(algorithm, devices, n_workers, max_w, max_h, &r, err, err_len)) return rc;
+    const int rc = dfb_list_run(r, clips, n_clips, step, bound, chunk_flows, queue, done, user, stats, err, err_len);
+    dfb_list_close(r);
+    return rc;
 }
 
 }  // extern "C"

@@ -298,21 +298,30 @@ struct TileCtx {
 // One primal + dual iteration of a tile visit.  EDGE: the tile contains the last image column or row (mirror handling
 // for the index-clamped forward differences); ERR: accumulate this thread's share of sum(diff) of the primal step.
 // Interior tiles in the middle of an epoch (the common case) instantiate neither.
+//
+// Order inside a warp (rows r = 0 .. RPT-1 of its block):   P0 | P1 D0 | P2 D1 | P3 D2 | D3
+// The dual step of row r needs the new u of rows r and r+1 only, and the primal step of row r+1 needs the OLD p of row r,
+// so D(r) can follow P(r+1) directly.  That puts the MUFU-bound dual arithmetic of one row next to the FMA-bound primal
+// arithmetic of the next in one instruction stream (neighbouring warps are forced into near lock-step by their
+// dependencies, so with "all primal, then all dual" every warp of the SM sat in the same phase and the two pipes took
+// turns idling).  It also shortens the cross-warp chain: the warp above needs only this warp's P0 for its D3, and this
+// warp's next P0 needs only the D3 of the warp above.
 template <bool EDGE, bool ERR>
 __device__ __forceinline__ void tile_iteration(Smem &sm, const TileCtx &t, const Tvl1Consts &c, int it, float4 (&p11)[RPT], float4 (&p12)[RPT],
                                                float4 (&p21)[RPT], float4 (&p22)[RPT], float &err) {
     volatile int *prog = sm.prog;
     const int so0 = t.so0, lane = t.lane, wq = t.wq;
-    // -------- primal: u <- u + d(rho) + theta * div p ------------------------------------------
     // p above the region's first row: the image border (p = 0) for tile row 0, halo garbage otherwise
     float4 up12 = zero4(), up22 = zero4();
     if (wq > 0) {
-        if (t.flagsync) wait_ge(&prog[wq - 1], t.base + 2 * it);
+        if (t.flagsync) wait_ge(&prog[wq - 1], t.base + 2 * it);  // D3 of the previous iteration of the warp above
         up12 = *reinterpret_cast<const float4 *>(&sm.p_bot[0][wq - 1][4 * lane]);
         up22 = *reinterpret_cast<const float4 *>(&sm.p_bot[1][wq - 1][4 * lane]);
     }
+    float4 c1 = zero4(), c2 = zero4();  // new u of the previous row (the dual step's centre row)
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
+        // -------- primal, row r: u <- u + d(rho) + theta * div p ---------------------------------
         const int so = so0 + r * TW;
         const float4 ix = *reinterpret_cast<const float4 *>(&sm.consts[0][so]);
         const float4 iy = *reinterpret_cast<const float4 *>(&sm.consts[1][so]);
@@ -324,7 +333,7 @@ __device__ __forceinline__ void tile_iteration(Smem &sm, const TileCtx &t, const
         float l21 = __shfl_up_sync(0xffffffffu, p21[r].w, 1);
         if (lane == 0) l11 = l21 = 0.f;  // region edge: image border (p = 0) for tile column 0, halo otherwise
         float4 n1, n2;
-        tvl1_primal_row(ix, iy, gq, rc, o1, o2, p11[r], l11, p12[r], up12, p21[r], l21, p22[r], up22, c, n1, n2);
+        tvl1_primal_row(ix, iy, gq, rc, o1, o2, p11[r], l11, p12[r], r == 0 ? up12 : p12[r - 1], p21[r], l21, p22[r], r == 0 ? up22 : p22[r - 1], c, n1, n2);
         if (ERR) {
             const int ry = RPT * wq + r;
             if (t.lane_in && ry >= t.ry_lo && ry < t.ry_hi && r < t.rows_left) {
@@ -342,35 +351,36 @@ __device__ __forceinline__ void tile_iteration(Smem &sm, const TileCtx &t, const
                 if (t.jlast == 2) { n1.w = n1.z; n2.w = n2.z; }
             }
             if (t.edge_y && r > 0 && r - 1 == t.rbot) {  // first out-of-image row: a copy of the last image row
-                n1 = *reinterpret_cast<const float4 *>(&sm.u[0][so - TW]);
-                n2 = *reinterpret_cast<const float4 *>(&sm.u[1][so - TW]);
+                n1 = c1;
+                n2 = c2;
             }
         }
         st4(&sm.u[0][so], n1);
         st4(&sm.u[1][so], n2);
-        up12 = p12[r];
-        up22 = p22[r];
-    }
-    signal(&prog[wq], t.base + 2 * it + 1);
-    if (!t.flagsync) __syncthreads();
-    // -------- dual: p <- (p + taut * grad u) / (1 + taut * |grad u|) ----------------------------
-    float4 c1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0]);
-    float4 c2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0]);
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        float4 d1, d2;
-        if (r < RPT - 1) {
-            d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + (r + 1) * TW]);
-            d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + (r + 1) * TW]);
+        if (r == 0) {
+            signal(&prog[wq], t.base + 2 * it + 1);  // row 0 of the new u is what the warp above waits for
+            if (!t.flagsync) __syncthreads();
         } else {
-            d1 = c1;  // region's last row: halo, or the mirrored image border
-            d2 = c2;
-            if (wq < kWarps - 1) {
-                if (t.flagsync) wait_ge(&prog[wq + 1], t.base + 2 * it + 1);
-                if (!(EDGE && t.edge_y && t.rbot == RPT - 1)) {
-                    d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
-                    d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
-                }
+            // -------- dual, row r-1: p <- (p + taut * grad u) / (1 + taut * |grad u|) ------------
+            float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
+            float r2 = __shfl_down_sync(0xffffffffu, c2.x, 1);
+            if (EDGE && t.edge_x && t.jlast == 3) {
+                r1 = c1.w;
+                r2 = c2.w;
+            }
+            tvl1_dual_row(c1, c2, n1, n2, r1, r2, c.taut, p11[r - 1], p12[r - 1], p21[r - 1], p22[r - 1]);
+        }
+        c1 = n1;
+        c2 = n2;
+    }
+    // -------- dual, last row: the row below belongs to the next warp (its P0 of this iteration) ----
+    {
+        float4 d1 = c1, d2 = c2;  // region's last row: halo, or the mirrored image border
+        if (wq < kWarps - 1) {
+            if (t.flagsync) wait_ge(&prog[wq + 1], t.base + 2 * it + 1);
+            if (!(EDGE && t.edge_y && t.rbot == RPT - 1)) {
+                d1 = *reinterpret_cast<const float4 *>(&sm.u[0][so0 + RPT * TW]);
+                d2 = *reinterpret_cast<const float4 *>(&sm.u[1][so0 + RPT * TW]);
             }
         }
         float r1 = __shfl_down_sync(0xffffffffu, c1.x, 1);
@@ -379,9 +389,7 @@ __device__ __forceinline__ void tile_iteration(Smem &sm, const TileCtx &t, const
             r1 = c1.w;
             r2 = c2.w;
         }
-        tvl1_dual_row(c1, c2, d1, d2, r1, r2, c.taut, p11[r], p12[r], p21[r], p22[r]);
-        c1 = d1;
-        c2 = d2;
+        tvl1_dual_row(c1, c2, d1, d2, r1, r2, c.taut, p11[RPT - 1], p12[RPT - 1], p21[RPT - 1], p22[RPT - 1]);
     }
     st4(&sm.p_bot[0][wq][4 * lane], p12[RPT - 1]);
     st4(&sm.p_bot[1][wq][4 * lane], p22[RPT - 1]);

@@ -35,13 +35,7 @@ class WorkQueue:
             self._q = C.c_void_p()
 
 
-def run_list(algorithm, devices, clips, step=1, bound=32, chunk_flows=0, queue=None, on_chunk=None, variant="default"):
-    """clips: list of sequences of uint8 [H,W] frames (one sequence per video; frames of one video share a size).
-    on_chunk(clip_index, device, first_flow, last_chunk, qx, qy, flows): called on the worker's thread when every output of
-    a chunk is in host memory (qx/qy: lists of uint8 [H,W] views when bound > 0, flows: list of float32 [H,W,2] views otherwise;
-    the views die when the callback returns).  `last_chunk` is the reference's FlowBuffer::last_buffer.
-    Returns a dict of dfb_list_stats."""
-    L = _lib.load(variant)
+def _pack_clips(clips):
     keep = []
     arr = (_lib.Clip * max(len(clips), 1))()
     for i, frames in enumerate(clips):
@@ -57,6 +51,12 @@ def run_list(algorithm, devices, clips, step=1, bound=32, chunk_flows=0, queue=N
         arr[i].n_frames = len(fr)
         arr[i].height, arr[i].width = (fr[0].shape if fr else (1, 1))
     shapes = [(arr[i].height, arr[i].width) for i in range(len(clips))]
+    return arr, shapes, keep
+
+
+def _callback(on_chunk, shapes):
+    if on_chunk is None:
+        return None
 
     def _cb(user, clip, dev, first, n, last, qx, qy, flows):
         h, w = shapes[clip]
@@ -68,7 +68,69 @@ def run_list(algorithm, devices, clips, step=1, bound=32, chunk_flows=0, queue=N
             vf = [np.ctypeslib.as_array(C.cast(flows[i], C.POINTER(C.c_float)), (h, w, 2)) for i in range(n)]
             on_chunk(clip, dev, first, bool(last), None, None, vf)
 
-    cb = _lib.CHUNK_DONE_FN(_cb) if on_chunk else None
+    return _lib.CHUNK_DONE_FN(_cb)
+
+
+def _stats(st):
+    W = st.workers
+    return {"clips": st.clips, "flows": st.flows, "frames": st.frames, "seconds": st.seconds, "workers": W,
+            "clips_per_worker": list(st.clips_per_worker[:W]), "flows_per_worker": list(st.flows_per_worker[:W]),
+            "busy_seconds_per_worker": list(st.busy_seconds_per_worker[:W]),
+            "finish_seconds_per_worker": list(st.finish_seconds_per_worker[:W]),
+            "kernel_launches": st.kernel_launches, "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes}
+
+
+class ListRunner:
+    """Workers kept alive between lists (dfb_list_open / dfb_list_run / dfb_list_close): worker i owns an engine handle on
+    devices[i]; a device may appear more than once."""
+
+    def __init__(self, algorithm, devices, max_width, max_height, variant="default"):
+        self._L = _lib.load(variant)
+        self._r = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        err = C.create_string_buffer(512)
+        rc = self._L.dfb_list_open(algorithm.encode(), devs, len(devices), int(max_width), int(max_height), C.byref(self._r), err, 512)
+        if rc != _lib.DFB_OK:
+            self._r = None
+            raise RuntimeError(err.value.decode() or "dfb_list_open failed (%d)" % rc)
+
+    def run(self, clips, step=1, bound=32, chunk_flows=0, queue=None, on_chunk=None, packed=None):
+        """packed: the result of a previous pack(clips) (building the pointer tables of a long list takes a while)."""
+        arr, shapes, keep = packed if packed is not None else _pack_clips(clips)
+        cb = _callback(on_chunk, shapes)
+        st = _lib.ListStats()
+        err = C.create_string_buffer(512)
+        rc = self._L.dfb_list_run(self._r, arr, len(shapes), int(step), int(bound), int(chunk_flows), queue._q if queue is not None else None,
+                                  C.cast(cb, C.c_void_p) if cb else None, None, C.byref(st), err, 512)
+        if rc != _lib.DFB_OK:
+            raise RuntimeError(err.value.decode() or "dfb_list_run failed (%d)" % rc)
+        return _stats(st)
+
+    @staticmethod
+    def pack(clips):
+        return _pack_clips(clips)
+
+    def close(self):
+        if getattr(self, "_r", None):
+            self._L.dfb_list_close(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_list(algorithm, devices, clips, step=1, bound=32, chunk_flows=0, queue=None, on_chunk=None, variant="default"):
+    """clips: list of sequences of uint8 [H,W] frames (one sequence per video; frames of one video share a size).
+    on_chunk(clip_index, device, first_flow, last_chunk, qx, qy, flows): called on the worker's thread when every output of
+    a chunk is in host memory (qx/qy: lists of uint8 [H,W] views when bound > 0, flows: list of float32 [H,W,2] views otherwise;
+    the views die when the callback returns).  `last_chunk` is the reference's FlowBuffer::last_buffer.
+    Returns a dict of dfb_list_stats."""
+    L = _lib.load(variant)
+    arr, shapes, keep = _pack_clips(clips)
+    cb = _callback(on_chunk, shapes)
     devs = (C.c_int * len(devices))(*devices)
     st = _lib.ListStats()
     err = C.create_string_buffer(512)
@@ -76,8 +138,4 @@ def run_list(algorithm, devices, clips, step=1, bound=32, chunk_flows=0, queue=N
                         queue._q if queue is not None else None, C.cast(cb, C.c_void_p) if cb else None, None, C.byref(st), err, 512)
     if rc != _lib.DFB_OK:
         raise RuntimeError(err.value.decode() or "dfb_run_list failed (%d)" % rc)
-    W = st.workers
-    return {"clips": st.clips, "flows": st.flows, "frames": st.frames, "seconds": st.seconds, "workers": W,
-            "clips_per_worker": list(st.clips_per_worker[:W]), "flows_per_worker": list(st.flows_per_worker[:W]),
-            "busy_seconds_per_worker": list(st.busy_seconds_per_worker[:W]),
-            "finish_seconds_per_worker": list(st.finish_seconds_per_worker[:W])}
+    return _stats(st)

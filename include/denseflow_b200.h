@@ -11,7 +11,8 @@
  * rethrows as std::runtime_error (reference behaviour: message + exit 1, tools/denseflow.cpp:93-96).
  * A handle is single-threaded (reference: one thread calls create/calc/release,
  * include/dense_flow.h:78); handles on different threads/devices are independent.  Every call
- * selects the handle's device itself.
+ * selects the handle's device itself.  A handle owns ONE set of workspace (pyramid slots, lanes): successive calls that
+ * take a stream must be stream-ordered with respect to each other (same stream, or the caller's events between them).
  */
 #ifndef DENSEFLOW_B200_H
 #define DENSEFLOW_B200_H
@@ -112,6 +113,18 @@ int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, in
 /* Stand-alone quantiser on device buffers (src/common.cpp:4-16).  flow_xy pitch in bytes. */
 int dfb_quantise_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, int width, int height, int bound,
                         uint8_t *qx, uint8_t *qy, size_t q_pitch, void *stream);
+
+/*
+ * The packed-PNG flow format on device buffers.  Replaces convertFlowToPngImage (src/common.cpp:18-46), the
+ * arithmetic behind `-st=png` (encodeFlowMapPng :66-71 then imencode(".png")s the result on the host): per-component
+ * minMaxLoc, bound = min(1020, ceil(min(extent, max|v|) * 128/127 / 4) * 4) (+4 when divisible by 8), x and y as
+ * convertTo(CV_8U, 128/bound, 128) [one float fused multiply-add, round-half-even, saturate — OpenCV's vector path], and a
+ * third channel holding bound_x/4 in rows 0..h/2 and bound_y/4 below.  bgr: packed 3 bytes per pixel (x, y, bounds).
+ * bounds_xy_host (optional, 2 doubles): receives bound_x, bound_y — passing it makes the call block on the stream.
+ * -st=h5 stays what it is in a build without HDF5: "HDF5 support is not enabled, pls recompile" (:241) — a host writer.
+ */
+int dfb_flow_to_png_image_device(dfb_handle *h, const float *flow_xy, size_t flow_pitch, int width, int height, uint8_t *bgr,
+                                  size_t bgr_pitch, double *bounds_xy_host, void *stream);
 
 /*
  * Frame preparation on device buffers — what the reference's decode stage does on the CPU to every
@@ -250,9 +263,18 @@ typedef struct {
     uint64_t clips_per_worker[DFB_LIST_MAX_WORKERS], flows_per_worker[DFB_LIST_MAX_WORKERS];
     double busy_seconds_per_worker[DFB_LIST_MAX_WORKERS];   /* time spent inside clips */
     double finish_seconds_per_worker[DFB_LIST_MAX_WORKERS]; /* when the worker ran out of work (tail imbalance) */
+    uint64_t kernel_launches, h2d_bytes, d2h_bytes;         /* summed over the workers' engine handles */
 } dfb_list_stats;
 int dfb_run_list(const char *algorithm, const int *devices, int n_workers, const dfb_clip *clips, int n_clips, int step, int bound,
                  int chunk_flows, dfb_queue *queue, dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len);
+/* The same with the workers (engine handles, pinned output rings) kept alive between lists: dfb_run_list is
+ * dfb_list_open + dfb_list_run + dfb_list_close.  err/err_len: optional buffer for the failure message. */
+typedef struct dfb_list_runner dfb_list_runner;
+int dfb_list_open(const char *algorithm, const int *devices, int n_workers, int max_width, int max_height, dfb_list_runner **out, char *err,
+                  size_t err_len);
+int dfb_list_run(dfb_list_runner *r, const dfb_clip *clips, int n_clips, int step, int bound, int chunk_flows, dfb_queue *queue,
+                 dfb_chunk_done_fn done, void *user, dfb_list_stats *stats, char *err, size_t err_len);
+void dfb_list_close(dfb_list_runner *r);
 
 #ifdef __cplusplus
 }
