@@ -160,19 +160,40 @@ def usable_cores():
 
 def _cpu_worker(job):
     alg, a, b, threads = job
+    if alg == "farn":
+        # BASELINE.json configs[0] / BASELINE.md R1: OpenCV's own CPU Farneback with the create() defaults of
+        # src/denseflow_gpu.cpp:301 — effectively single-threaded, so one pair per core
+        import cv2
+        cv2.setNumThreads(1)
+        cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 5, 13, 10, 5, 1.1, 0)
+        return 1
     from oracle import pyoracle as O
     O.lib().orc_set_num_threads(threads)
-    (O.tvl1_calc if alg == "tvl1" else O.farn_calc)(a, b)
+    O.tvl1_calc(a, b)
     return 1
+
+
+def cpu_split(alg):
+    """(processes, threads per process) for the CPU arm: tvl1 = oracle port, OpenMP loops stop scaling past ~8 threads;
+    farn = cv2.calcOpticalFlowFarneback, one single-threaded pair per core."""
+    cores = usable_cores()
+    threads = 1 if alg == "farn" else min(8, cores)
+    return max(1, cores // threads), threads
+
+
+def cpu_kind_note(alg):
+    if alg == "farn":
+        return ("cv2.calcOpticalFlowFarneback(a,b,None,0.5,5,13,10,5,1.1,0) (OpenCV %s CPU, the algorithm and defaults of "
+                "cv::cuda::FarnebackOpticalFlow::create(); differs from the CUDA class only in the resize sampling convention)" % __import__("cv2").__version__)
+    return ("CPU restatement of the CUDA algorithm (oracle/, -O2 scalar C + OpenMP: a soft baseline): OpenCV CPU DualTVL1 (contrib) is not "
+            "installed and the reference itself needs OpenCV-CUDA")
 
 
 def cpu_port_throughput(alg, frames, n_pairs_per_proc, warm=True):
     """The CPU restatement on ALL host cores: the per-pair OpenMP loops stop scaling long before 64 threads, so the
     cores are split into P processes x T threads working on different pairs concurrently (aggregate pairs/s)."""
     import multiprocessing as mp
-    cores = usable_cores()
-    threads = min(8, cores)
-    procs = max(1, cores // threads)
+    procs, threads = cpu_split(alg)
     n = len(frames) - 1
     jobs = [(alg, frames[i % n], frames[i % n + 1], threads) for i in range(procs * n_pairs_per_proc)]
     ctx = mp.get_context("spawn")
@@ -187,9 +208,8 @@ def cpu_port_throughput(alg, frames, n_pairs_per_proc, warm=True):
         pool.close()
         pool.join()
     return {"value": len(jobs) / dt, "unit": "pairs/s", "cores": procs * threads, "kind": "port",
-            "sample": "%d pairs of the same stream (%d processes x %d OpenMP threads, %d pairs each, after one warm-up pair per process); "
-                      "CPU restatement of the CUDA algorithm (oracle/): OpenCV CPU DualTVL1 (contrib) is not installed and the reference "
-                      "itself needs OpenCV-CUDA" % (len(jobs), procs, threads, n_pairs_per_proc)}
+            "sample": "%d pairs of the same stream (%d processes x %d threads, %d pairs each, after one warm-up pair per process); %s"
+                      % (len(jobs), procs, threads, n_pairs_per_proc, cpu_kind_note(alg))}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -212,9 +232,7 @@ def run_reference(args, alg, W, H, seed, desc):
     import multiprocessing as mp
     P = args.pairs
     frames = make_stream(W, H, NWIN * (P + 1), seed, 0).reshape(NWIN, P + 1, H, W)
-    cores_all = usable_cores()
-    threads = min(8, cores_all)
-    procs = max(1, cores_all // threads)
+    procs, threads = cpu_split(alg)
     cores = procs * threads
     step_jobs = [[(alg, frames[w][i], frames[w][i + 1], threads) for i in range(P)] for w in range(NWIN)]
     ctx = mp.get_context("spawn")
@@ -231,15 +249,14 @@ def run_reference(args, alg, W, H, seed, desc):
         pool.join()
     value = args.steps * P / dt
     sample = ("each step = the %d pairs of one input window of the workload stream (the GPU arm's frames), spread over %d processes x %d "
-              "OpenMP threads = all %d usable host cores" % (P, procs, threads, cores))
+              "threads = %d usable host cores; %s" % (P, procs, threads, cores, cpu_kind_note(alg)))
     line = {
         "impl": "reference", "metric": METRIC if args.workload == "tvl1_1080p" else "%s flow-pairs/sec at %dx%d" % (alg, W, H),
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": bench_config(args, alg, W, H, desc),
-        "note": "CPU restatement of the reference's CUDA algorithm (oracle port, -O2 scalar C + OpenMP: a soft baseline); the reference "
-                "itself needs OpenCV-CUDA+Boost and cannot be built in this image; OpenCV CPU DualTVL1 (contrib) is not installed",
+        "note": cpu_kind_note(alg) + "; the reference itself needs OpenCV-CUDA+Boost and cannot be built in this image",
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -392,8 +409,7 @@ def main():
     flows_pin = torch.empty((P, H, W, 2), dtype=torch.float32).pin_memory()
 
     eng = d.create(alg, local_rank, W, H)
-    if alg == "tvl1":
-        eng.set("time_kernels", 1)
+    eng.set("time_kernels", 1)
     stream = torch.cuda.current_stream(dev)
 
     def step_device(i):
@@ -471,6 +487,25 @@ def main():
             "pixel_visits_per_pair": c["pixel_chunks"] / max(npairs, 1),
             "kernel_share_of_step": kt / dt_dev,
         }
+
+    if alg == "farn" and c["timed_kernel_launches"]:
+        peak, peak_src = load_peaks()
+        kt = c["timed_kernel_ns"] / 1e9
+        nl = c["timed_kernel_launches"]
+        npairs = c["timed_kernel_pairs"]
+        # fused iteration kernel (box 13x13 -> 2x2 solve -> rebuild M): read M(5) + R0(5) + R1(5, gathered) + write M(5) + flow(2)
+        # = 88 B per level pixel and iteration (fused formulation); pixel_iters is counted by the engine
+        b_alg = 88.0 * c["pixel_iters"]
+        achieved = b_alg / kt / 1e9
+        t = ncu_traffic(args.workload, min(8, P))  # pairs per launch = the engine's batch of up to 8 pairs (blockIdx.z)
+        roof = {"bound": "hbm", "kernel": "k_box_solve_update<6> (13x13 box mean of M -> 2x2 solve -> rebuild M, one launch per iteration and level, up to 8 pairs per launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": t[0], "traffic_source": t[1],
+                "peak_source": peak_src,
+                "formulation": "SURVEY §8d fused-iteration figure: 88 B per level pixel and iteration x executed pixel-iterations (engine counter), "
+                               "over the CUDA-event time of the iteration launches only (one event pair per level); the last iteration of a level "
+                               "skips the rebuild (48 B) and is counted at 88 B too, i.e. the figure is an upper bound by ~4 %",
+                "algorithmic_bytes_per_launch": b_alg / nl, "avg_launch_ms": kt / nl * 1e3,
+                "launches": nl, "pixel_iters_per_pair": c["pixel_iters"] / max(npairs, 1), "kernel_share_of_step": kt / dt_dev}
 
     # ---------------- stand-alone primal / dual kernels of the unfused schedule vs the HBM roofline ------------
     kernels = None

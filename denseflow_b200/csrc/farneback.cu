@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "tma.cuh"
 #include "tvl1.cuh"
 
 namespace dfb {
@@ -263,28 +264,24 @@ constexpr int BW = 32;
 #define DFB_FARN_BH 16
 #endif
 constexpr int BH = DFB_FARN_BH;  // 16: 512-pixel tiles, 38 KB of shared memory, 5 CTAs / SM (the kernel is latency-bound)
+// The staged window of one M plane: (BH + 2 HALF) rows x RW columns, RW = BW + 2 HX with HX >= HALF rounded up so that the window
+// starts on a 32-byte boundary of the plane row (x0 - HX, x0 a multiple of 32) and its rows are 16-byte multiples (TMA box rule).
+#ifndef DFB_FARN_HX
+#define DFB_FARN_HX 8
+#endif
+constexpr int HX = DFB_FARN_HX;
+constexpr int RW = BW + 2 * HX;
+constexpr int kBoxPlaneSlot = ((RW * (BH + 12) + 31) / 32) * 32;  // floats per staged window, a multiple of 128 bytes (TMA destination)
 
+// The part of the iteration that works out of shared memory: raw = the five (BH + 2 HALF) x (BW + 2 HALF) windows of M
+// (index-clamped), vs = scratch for the vertical sums.  Shared by the LDG-staged and the TMA-staged kernel.
 template <int HALF>
-__global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
-    const PairArgs &a = args.p[blockIdx.z];
-    const Plane5 Min = a.M[mb], Mout = a.M[mb ^ 1], R0 = a.R0, R1 = a.R1;
+__device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPlaneSlot] */, float (*vs)[BH][BW + 2 * HALF], const PairArgs &a, int mb,
+                                                 int rebuild, int x0, int y0, int tid) {
+    const Plane5 Mout = a.M[mb ^ 1], R0 = a.R0, R1 = a.R1;
     const Plane fxp = a.fx, fyp = a.fy;
-    constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
-    extern __shared__ float box_smem[];
-    float(*raw)[sh][sw] = reinterpret_cast<float(*)[sh][sw]>(box_smem);               // [5][sh][sw]
-    float(*vs)[BH][sw] = reinterpret_cast<float(*)[BH][sw]>(box_smem + 5 * sh * sw);  // [5][BH][sw]
-    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
-    const int w = Min.w, h = Min.h, pitch = Min.pitch;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < sh * sw; i += 256) {
-        const int ty = i / sw, tx = i - ty * sw;
-        const int y = max(0, min(y0 + ty - HALF, h - 1));
-        const int x = max(0, min(x0 + tx - HALF, w - 1));
-        const size_t o = (size_t)y * pitch + x;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) raw[k][ty][tx] = Min.p[k][o];
-    }
-    __syncthreads();
+    constexpr int sw = BW + 2 * HALF;
+    const int w = Mout.w, h = Mout.h, pitch = Mout.pitch;
     // vertical sums, register-blocked: one task = 4 vertically consecutive outputs of one column and plane
     // (16 window reads for 4 sums instead of 52); each sum keeps the reference's order (centre, then symmetric
     // pairs outward).  Clamped rows are materialised in the window, which equals clamping the tap's row index.
@@ -294,7 +291,7 @@ __global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant_
         const int g = rest % (BH / VG), k = rest / (BH / VG);
         float v[VG + 2 * HALF];
 #pragma unroll
-        for (int q = 0; q < VG + 2 * HALF; ++q) v[q] = raw[k][g * VG + q][tx];
+        for (int q = 0; q < VG + 2 * HALF; ++q) v[q] = raw[k * kBoxPlaneSlot + (g * VG + q) * RW + tx + (HX - HALF)];
 #pragma unroll
         for (int o = 0; o < VG; ++o) {
             float acc = v[o + HALF];
@@ -374,6 +371,94 @@ __global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant_
         }
     }
 }
+
+template <int HALF>
+__global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const Plane5 Min = a.M[mb];
+    constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
+    static_assert(RW * sh <= kBoxPlaneSlot && HX >= HALF, "window fits its slot");
+    extern __shared__ float box_smem[];
+    float *raw = box_smem;                                                                    // [5][kBoxPlaneSlot]
+    float(*vs)[BH][sw] = reinterpret_cast<float(*)[BH][sw]>(box_smem + 5 * kBoxPlaneSlot);  // [5][BH][sw]
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    const int w = Min.w, h = Min.h, pitch = Min.pitch;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < sh * RW; i += 256) {
+        const int ty = i / RW, tx = i - ty * RW;
+        const int y = max(0, min(y0 + ty - HALF, h - 1));
+        const int x = max(0, min(x0 + tx - HX, w - 1));
+        const size_t o = (size_t)y * pitch + x;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) raw[k * kBoxPlaneSlot + i] = Min.p[k][o];
+    }
+    __syncthreads();
+    box_tile_compute<HALF>(raw, vs, a, mb, rebuild, x0, y0, tid);
+}
+
+// The same iteration as a persistent kernel with TMA-staged, double-buffered windows (the default): a CTA walks the tile
+// list of the whole batch (pairs x tile rows x tile columns); while it sums / solves tile i out of one shared-memory
+// stage, one thread has already asked the TMA unit for the five windows of tile i + 1 (cp.async.bulk.tensor.2d, completion
+// on an mbarrier, zero fill outside the image).  Index-clamped borders: tiles that touch the image border copy the
+// nearest in-image entry of the window into the zero-filled ones (border tiles only), which reproduces the clamped
+// reads of the LDG kernel bit for bit.
+template <int HALF>
+struct BoxTmaSmem {
+    float raw[2][5][kBoxPlaneSlot];
+    float vs[5][BH][BW + 2 * HALF];
+    unsigned long long bar[2];
+};
+
+template <int HALF>
+__global__ void __launch_bounds__(256) k_box_solve_update_tma(const __grid_constant__ FarnBatchArgs args, const char *maps, int nb, int ntx, int nty,
+                                                              int mb, int rebuild) {
+    constexpr int sh = BH + 2 * HALF;
+    static_assert(RW * sh <= kBoxPlaneSlot && (RW * 4) % 16 == 0 && HX >= HALF, "window fits its slot, rows are 16-byte multiples");
+    extern __shared__ __align__(128) unsigned char box_tma_smem[];
+    BoxTmaSmem<HALF> &sm = *reinterpret_cast<BoxTmaSmem<HALF> *>(box_tma_smem);
+    const int tid = threadIdx.x;
+    const int per = ntx * nty, total = nb * per;
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+    }
+    __syncthreads();
+    auto issue = [&](int t, int stage) {  // thread 0: the five windows of tile t -> stage
+        const int z = t / per, r = t - z * per, ty = r / ntx, tx = r - ty * ntx;
+        const char *m = maps + (size_t)((z * 2 + mb) * 5) * kTensorMapBytes;
+        mbar_expect_tx(&sm.bar[stage], 5u * RW * sh * (unsigned)sizeof(float));
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tma_load_2d(sm.raw[stage][k], m + k * kTensorMapBytes, tx * BW - HX, ty * BH - HALF, &sm.bar[stage]);
+    };
+    int t = blockIdx.x;
+    if (t < total && tid == 0) issue(t, 0);
+    for (int i = 0; t < total; ++i, t += gridDim.x) {
+        const int stage = i & 1;
+        if (t + (int)gridDim.x < total && tid == 0) issue(t + gridDim.x, stage ^ 1);  // every reader of that stage passed the barrier below
+        mbar_wait(&sm.bar[stage], (i >> 1) & 1);
+        const int z = t / per, r = t - z * per, tyi = r / ntx, txi = r - tyi * ntx;
+        const PairArgs &a = args.p[z];
+        const int x0 = txi * BW, y0 = tyi * BH;
+        const int w = a.M[mb].w, h = a.M[mb].h;
+        if (x0 < HX || y0 < HALF || x0 + BW + HX > w || y0 + BH + HALF > h) {
+            for (int j = tid; j < sh * RW; j += 256) {
+                const int ty = j / RW, tx = j - ty * RW;
+                const int gy = y0 + ty - HALF, gx = x0 + tx - HX;
+                const int cy = max(0, min(gy, h - 1)), cx = max(0, min(gx, w - 1));
+                if (cy != gy || cx != gx) {
+                    const int src = (cy - y0 + HALF) * RW + (cx - x0 + HX);  // an in-image entry: never written by this loop
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) sm.raw[stage][k][j] = sm.raw[stage][k][src];
+                }
+            }
+            __syncthreads();
+        }
+        box_tile_compute<HALF>(&sm.raw[stage][0][0], sm.vs, a, mb, rebuild, x0, y0, tid);
+        fence_proxy_async();  // this thread's reads of the stage are ordered before the TMA writes a later iteration asks for
+        __syncthreads();
+    }
+}
+
 // level start: flow = 0 at the coarsest level, else resize(prev) * (1/pyrScale) (B.2), both components, batched
 __global__ void __launch_bounds__(256) k_flow_init(const __grid_constant__ FarnBatchArgs args, int first, float rfx, float rfy, float mul) {
     const PairArgs &a = args.p[blockIdx.z];
@@ -419,7 +504,7 @@ __global__ void __launch_bounds__(256) k_farn_merge(const __grid_constant__ Farn
     row[x] = make_float2(u, v);
 }
 
-constexpr size_t kBoxSmemBytes = (size_t)(5 * (BH + 12) * (BW + 12) + 5 * BH * (BW + 12)) * sizeof(float);
+constexpr size_t kBoxSmemBytes = (size_t)(5 * kBoxPlaneSlot + 5 * BH * (BW + 12)) * sizeof(float);
 
 struct FarnParams {
     int num_levels = 5;
@@ -546,11 +631,22 @@ class Farneback final : public FlowAlgorithm {
         ensure_lanes(1);
         DFB_CUDA(cudaFuncSetAttribute(k_gauss_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, GT * (GT + 2 * kMaxHalf) * 4));
         DFB_CUDA(cudaFuncSetAttribute(k_box_solve_update<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBoxSmemBytes));
+        DFB_CUDA(cudaFuncSetAttribute(k_box_solve_update_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BoxTmaSmem<6>)));
+        DFB_CUDA(cudaFuncSetAttribute(k_box_solve_update_tma<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0, sms = 0;
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_box_solve_update_tma<6>, 256, sizeof(BoxTmaSmem<6>)));
+        DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+        persistent_ctas_ = std::max(1, per_sm) * sms;
+        DFB_CUDA(cudaMalloc(&d_maps_, kMapBytes));
     }
     ~Farneback() override {
         cudaSetDevice(device_);
         for (auto p : extra_slots_) cudaFree(p);
         for (auto &l : lanes_) cudaFree(l.own);
+        if (d_maps_) cudaFree(d_maps_);
+        for (auto &e : timing_ev_)
+            for (auto ev : e)
+                if (ev) cudaEventDestroy(ev);
     }
     const char *name() const override { return "farn"; }
     int num_slots() const override { return (int)slots_.size(); }
@@ -559,6 +655,7 @@ class Farneback final : public FlowAlgorithm {
             float *p = nullptr;
             DFB_CUDA(cudaMalloc(&p, slot_elems_ * sizeof(float)));
             DFB_CUDA(cudaMemset(p, 0, slot_elems_ * sizeof(float)));
+            DFB_CUDA(cudaDeviceSynchronize());  // null-stream memset vs the handle's non-blocking streams
             extra_slots_.push_back(p);
             slots_.push_back(p);
         }
@@ -569,6 +666,8 @@ class Farneback final : public FlowAlgorithm {
         else if (k == "poly_sigma") prm_.poly_sigma = v;
         else if (k == "pyr_scale") return v == 0.5;  // level geometry and the slot layout assume the default
         else if (k == "win_size" || k == "poly_n") return (k == "win_size" ? v == 13 : v == 5);  // compiled-in stencils
+        else if (k == "time_kernels") time_kernels_ = v != 0;
+        else if (k == "use_tma") use_tma_ = v != 0;
         else return false;
         return true;
     }
@@ -579,8 +678,35 @@ class Farneback final : public FlowAlgorithm {
         else if (k == "num_iters") *v = prm_.num_iters;
         else if (k == "poly_n") *v = prm_.poly_n;
         else if (k == "poly_sigma") *v = prm_.poly_sigma;
+        else if (k == "time_kernels") *v = time_kernels_;
+        else if (k == "use_tma") *v = use_tma_;
         else return false;
         return true;
+    }
+
+    // CUDA-event timing of the dominant kernel (k_box_solve_update): one event pair around the iteration launches of every
+    // level (nothing else is enqueued between them), drained lazily
+    void drain_timing() {
+        for (int i = 0; i < timing_used_; ++i) {
+            DFB_CUDA(cudaEventSynchronize(timing_ev_[i][1]));
+            float ms = 0.f;
+            DFB_CUDA(cudaEventElapsedTime(&ms, timing_ev_[i][0], timing_ev_[i][1]));
+            timed_ns_ += (uint64_t)((double)ms * 1e6);
+        }
+        timing_used_ = 0;
+    }
+    void kernel_timing(uint64_t *launches_, uint64_t *ns, uint64_t *pairs) override {
+        drain_timing();
+        *launches_ = timed_launches_;
+        *ns = timed_ns_;
+        *pairs = timed_pairs_;
+    }
+    void reset_counters() override {
+        drain_timing();
+        launches = 0;
+        pixel_iters = 0;
+        pixel_chunks = 0;
+        timed_launches_ = timed_ns_ = timed_pairs_ = 0;
     }
 
     // per-frame work (B.2, B.3): u8 -> fp32, then for every level: Gaussian blur of the FULL-resolution frame,
@@ -630,9 +756,11 @@ class Farneback final : public FlowAlgorithm {
 
     void solve_batch(const PairJob *jobs, int count, int w, int h, cudaStream_t s) override {
         const LevelSet ls = levels_for(w, h, false);
+        timed_pairs_ += time_kernels_ ? count : 0;
         for (int j0 = 0; j0 < count; j0 += kMaxFarnBatch) {
             const int nb = std::min(kMaxFarnBatch, count - j0);
             ensure_lanes(nb);
+            if (use_tma_) ensure_tensor_maps(ls);
             int cur = 0;
             FarnBatchArgs args{};
             for (int l = 0; l < ls.n; ++l) {
@@ -670,12 +798,34 @@ class Farneback final : public FlowAlgorithm {
                 k_update_matrices<<<g8, b8, 0, s>>>(args, mb);
                 DFB_KERNEL_CHECK();
                 launches += 2;
+                pixel_iters += (uint64_t)L.w * L.h * prm_.num_iters * nb;
+                if (time_kernels_) {
+                    if (timing_used_ == kTimingRing) drain_timing();
+                    if (!timing_ev_[0][0])
+                        for (int i = 0; i < kTimingRing; ++i) {
+                            DFB_CUDA(cudaEventCreate(&timing_ev_[i][0]));
+                            DFB_CUDA(cudaEventCreate(&timing_ev_[i][1]));
+                        }
+                    DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][0], s));
+                }
                 for (int it = 0; it < prm_.num_iters; ++it) {
                     const int rebuild = it < prm_.num_iters - 1;
-                    k_box_solve_update<6><<<dim3(ceil_div(L.w, BW), ceil_div(L.h, BH), nb), 256, kBoxSmemBytes, s>>>(args, mb, rebuild);
+                    if (use_tma_) {
+                        const int ntx = ceil_div(L.w, BW), nty = ceil_div(L.h, BH);
+                        const int grid = std::min(persistent_ctas_, ntx * nty * nb);
+                        k_box_solve_update_tma<6><<<grid, 256, sizeof(BoxTmaSmem<6>), s>>>(
+                            args, d_maps_ + (size_t)l * kMaxFarnBatch * 10 * kTensorMapBytes, nb, ntx, nty, mb, rebuild);
+                    } else {
+                        k_box_solve_update<6><<<dim3(ceil_div(L.w, BW), ceil_div(L.h, BH), nb), 256, kBoxSmemBytes, s>>>(args, mb, rebuild);
+                    }
                     DFB_KERNEL_CHECK();
                     ++launches;
                     mb ^= 1;
+                }
+                if (time_kernels_) {
+                    DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][1], s));
+                    ++timing_used_;
+                    timed_launches_ += prm_.num_iters;
                 }
                 if (l == ls.n - 1) {  // last processed level is full resolution (k = 0): merge -> CV_32FC2
                     k_farn_merge<<<g8, b8, 0, s>>>(args);
@@ -745,12 +895,39 @@ class Farneback final : public FlowAlgorithm {
         float *fx[2] = {}, *fy[2] = {};
     };
     std::vector<Lane> lanes_;
+    // TMA descriptors of the M planes: [level][lane][buffer][plane], rebuilt when the frame geometry or the lane count changes
+    static constexpr size_t kMapBytes = (size_t)kMaxLevels * kMaxFarnBatch * 10 * kTensorMapBytes;
+    char *d_maps_ = nullptr;
+    int maps_w_ = 0, maps_h_ = 0, maps_lanes_ = 0, maps_levels_ = 0;
+    int persistent_ctas_ = 148, use_tma_ = 1;
+    void ensure_tensor_maps(const LevelSet &ls) {
+        const Level &F = ls.lv[ls.n - 1];
+        if (maps_w_ == F.w && maps_h_ == F.h && maps_lanes_ == (int)lanes_.size() && maps_levels_ == ls.n) return;
+        std::vector<char> host(kMapBytes, 0);
+        for (int l = 0; l < ls.n; ++l)
+            for (int i = 0; i < (int)lanes_.size() && i < kMaxFarnBatch; ++i)
+                for (int b = 0; b < 2; ++b)
+                    for (int k = 0; k < 5; ++k)
+                        encode_tensor_map_2d(host.data() + (((size_t)l * kMaxFarnBatch + i) * 10 + b * 5 + k) * kTensorMapBytes, lanes_[i].M[b][k],
+                                             ls.lv[l].w, ls.lv[l].h, ls.lv[l].pitch, RW, BH + 12);
+        DFB_CUDA(cudaDeviceSynchronize());  // a launch with the previous descriptors may still be running
+        DFB_CUDA(cudaMemcpy(d_maps_, host.data(), host.size(), cudaMemcpyHostToDevice));
+        maps_w_ = F.w;
+        maps_h_ = F.h;
+        maps_lanes_ = (int)lanes_.size();
+        maps_levels_ = ls.n;
+    }
+    static constexpr int kTimingRing = 256;
+    cudaEvent_t timing_ev_[kTimingRing][2] = {};
+    int timing_used_ = 0, time_kernels_ = 0;
+    uint64_t timed_launches_ = 0, timed_ns_ = 0, timed_pairs_ = 0;
     void ensure_lanes(int n) {
         while ((int)lanes_.size() < n) {
             Lane l;
             const size_t pl = Slab::padded(plane_elems_, 4) / sizeof(float);
             DFB_CUDA(cudaMalloc(&l.own, 14 * pl * sizeof(float)));
             DFB_CUDA(cudaMemset(l.own, 0, 14 * pl * sizeof(float)));
+            DFB_CUDA(cudaDeviceSynchronize());  // null-stream memset vs the caller's (possibly non-blocking) stream
             float *c = l.own;
             for (int b = 0; b < 2; ++b)
                 for (int k = 0; k < 5; ++k) {

@@ -54,6 +54,9 @@ class Tvl1 final : public FlowAlgorithm {
         }
         if (stats_event_) cudaEventDestroy(stats_event_);
         if (pair_log_) cudaFreeHost(pair_log_);
+        for (auto &e : timing_ev_)
+            for (auto ev : e)
+                if (ev) cudaEventDestroy(ev);
     }
     const char *name() const override { return "tvl1"; }
     int num_slots() const override { return (int)slots_.size(); }

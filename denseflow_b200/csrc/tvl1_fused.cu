@@ -29,11 +29,10 @@
 // branch of the A.4 state machine and results are run-to-run deterministic.
 #include <cfloat>
 
-#include <cooperative_groups.h>
-#include <cuda.h>
 
 #include <mutex>
 
+#include "tma.cuh"
 #include "tvl1_fused.cuh"
 #include "tvl1_math.cuh"
 
@@ -76,37 +75,6 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers ---------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// 2-D tile load global -> shared, completion signalled on the mbarrier (zero fill outside the tensor)
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- grid barrier ---------------------------------------------------------------------------
 // sync[0] counts arrivals monotonically: barrier number b of a lane completes when it reaches b * G
@@ -700,26 +668,7 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
 }  // namespace
 
 void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pitch) {
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        DFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    static_assert(sizeof(CUtensorMap) == kTensorMapBytes, "CUtensorMap size");
-    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
-    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)TW, (cuuint32_t)TH};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims,
-                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    encode_tensor_map_2d(out, plane, w, h, pitch, TW, TH);
 }
 
 int fused_num_sms(int device) {

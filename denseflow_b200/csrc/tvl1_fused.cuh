@@ -2,6 +2,7 @@
 // between the host engine and the device code.
 #pragma once
 
+#include "tma.cuh"
 #include "tvl1.cuh"
 
 namespace dfb {
@@ -54,7 +55,6 @@ struct FusedJob {
 // GPU has SMs; running pairs side by side keeps every SM busy without touching a pair's arithmetic.
 constexpr int kFusedMaxLanes = 16;  // 16 jobs x ~1.4 KB of kernel parameters (limit 32 KB since CUDA 12.1)
 constexpr int kFusedMapsPerLevel = 8;
-constexpr int kTensorMapBytes = 128;  // sizeof(CUtensorMap)
 struct FusedBatch {
     int njobs, group;
     FusedJob job[kFusedMaxLanes];

@@ -18,15 +18,18 @@
  * recorded in SURVEY.md Appendix A (TV-L1) and Appendix B (Farneback).
  *
  * PINNING STATUS
- *   - quantiser:  pinned bit-exactly against the formula at src/common.cpp:6 (tests/golden/quantise_*.npy).
+ *   - quantiser:  pinned bit-exactly against the formula at src/common.cpp:6 (tests/golden/quantise_cases.npz, made by
+ *                 tests/golden/make_golden.py; checked in tests/test_oracle_cpu.py).
  *   - Farneback:  pinned against real OpenCV code that runs in this image —
  *                 cv2.calcOpticalFlowFarneback(a,b,None,0.5,5,13,10,5,1.1,0) — with the resize
  *                 convention switched to OpenCV-CPU's half-pixel centres (ORC_RESIZE_HALF_PIXEL);
- *                 see oracle/pin_farneback_cv2.py and tests/test_oracle_farneback.py.
+ *                 committed samples tests/golden/farneback_cv2_*.npz (tests/golden/make_golden.py) and a live comparison,
+ *                 both in tests/test_oracle_cpu.py.
  *   - TV-L1:      PARITY UNPINNED.  No OpenCV build with cudaoptflow / optflow exists in this
  *                 image or on the GPU box, the reference has no tests or golden vectors, and
  *                 the reference itself cannot be compiled here (needs OpenCV-CUDA, Boost).
- *                 The restatement is only self-consistency checked (analytic ground-truth flow).
+ *                 The restatement is only self-consistency checked (analytic ground-truth flow, an independently written
+ *                 numpy restatement oracle/tvl1_numpy.py, and the frozen regression fixture tests/golden/tvl1_oracle_256.npz).
  */
 #ifndef DENSEFLOW_ORACLE_H
 #define DENSEFLOW_ORACLE_H

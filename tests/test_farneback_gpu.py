@@ -69,3 +69,20 @@ def test_farneback_1080p_six_levels(oracle):
     ref = oracle.farn_calc(fr[0], fr[1])
     flow = _engine(1920, 1080).calc(fr[0], fr[1])
     assert synth.aee(flow, ref) <= AEE_TOL
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (360, 640), (720, 1280)])
+def test_tma_staged_iteration_is_bit_identical(shape):
+    """The persistent TMA-staged, double-buffered iteration kernel (default) and the LDG-staged one (use_tma = 0) read the same
+    windows: zero-filled out-of-image entries are replaced by the index-clamped value on border tiles.  Batches of several
+    pairs (the tile list walks pairs x rows x columns), odd sizes, partial tiles."""
+    h, w = shape
+    fr = synth.stream(h, w, 7, seed=40)
+    e0 = _engine(w, h)
+    e0.set("use_tma", 0)
+    e1 = _engine(w, h)
+    assert e1.get("use_tma") == 1
+    a = e0.calc_batch(list(fr), step=1)
+    b = e1.calc_batch(list(fr), step=1)
+    assert np.array_equal(a, b)
+    assert np.array_equal(b, e1.calc_batch(list(fr), step=1))  # and run to run (stage reuse, mbarrier phases)
