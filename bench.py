@@ -34,6 +34,7 @@ WORKLOADS = {
     "tvl1_340x256": ("tvl1", 340, 256, 100, "synthetic 340x256 clips, -a=tvl1 -s=1 (BASELINE.json configs[4])"),
     "tvl1_256": ("tvl1", 256, 256, 0, "synthetic 256x256 pair stream, -a=tvl1 -s=1 (BASELINE.json configs[1])"),
     "farn_720p": ("farn", 1280, 720, 2, "synthetic 1280x720 stream, -a=farn -s=1 (BASELINE.json configs[3])"),
+    "tvl1_455x256": ("tvl1", 455, 256, 1, "synthetic 455x256 frames (a 1080p video with -ns=256), -a=tvl1 -s=1"),
 }
 METRIC = "tvl1 flow-pairs/sec at 1920x1080"
 NWIN = 2  # distinct input windows of pairs+1 frames each, alternated between steps (both arms)
@@ -73,6 +74,9 @@ def parse():
     ap.add_argument("--list-distinct", type=int, default=8, help="distinct synthetic clips the list cycles through")
     ap.add_argument("--list-bound", type=int, default=32, help="-b of the CLI (default 32): the uint8 planes come back")
     ap.add_argument("--workers-per-gpu", type=int, default=2, help="list mode: host threads (engine handles) per GPU")
+    # the reference's per-batch chain minus decode / file IO: BGR frames -> gray -> resize -> flow -> quantise -> 2 JPEGs per pair
+    ap.add_argument("--chain", action="store_true", help="chain mode: dfb_process_bgr_batch_host on BGR frames of --chain-src size")
+    ap.add_argument("--chain-src", default="", help="WxH of the decoded BGR frames (default: the workload's size, i.e. no resize)")
     return ap.parse_args()
 
 
@@ -377,6 +381,94 @@ def run_list_mode(args, alg, W, H, seed, desc):
         pass
 
 
+def _cpu_chain_worker(job):
+    """The reference's CPU stages around the flow for one pair: cvtColor + resize of one new frame (src/denseflow_gpu.cpp:163-170)
+    and convertFlowToImage's output through two imencode(".jpg") calls (src/common.cpp:56-57)."""
+    import cv2
+    import numpy as np
+    bgr, size, qx, qy, reps = job
+    cv2.setNumThreads(1)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        g = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+        if size != (bgr.shape[1], bgr.shape[0]):
+            g = cv2.resize(g, size)
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        cv2.imencode(".jpg", qx)
+        cv2.imencode(".jpg", qy)
+    t2 = time.perf_counter()
+    return (t1 - t0) / reps, (t2 - t1) / reps
+
+
+def run_chain_mode(args, alg, W, H, seed, desc):
+    """--chain: the reference's per-batch chain minus decode and file IO through dfb_process_bgr_batch_host: pinned BGR frames in,
+    two JPEG bitstreams per pair out; (W, H) of the workload is the size the flow runs at, --chain-src the decoded frame size."""
+    import numpy as np
+    import torch
+    import denseflow_b200 as d
+    from denseflow_b200 import shard, synth
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    rank, local_rank, world = shard.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    SW, SH = (int(x) for x in args.chain_src.split("x")) if args.chain_src else (W, H)
+    P = args.pairs
+    gray = synth.stream(SH, SW, P + 1, seed + 1000 * rank, phase=7.0 * rank)
+    bgr_t = torch.from_numpy(np.stack([np.roll(gray, 2, 2), gray, 255 - np.roll(gray, 3, 1)], -1).copy()).pin_memory()
+    bgr = [bgr_t[i].numpy() for i in range(P + 1)]
+    e = d.create(alg, local_rank, W, H)
+    new_size = None if (SW, SH) == (W, H) else (W, H)
+    out = None
+    for _ in range(max(args.warmup, 1)):
+        out = e.process_bgr_batch(bgr, step=1, bound=20, new_size=new_size)
+    torch.cuda.synchronize(dev)
+    shard.barrier()
+    e.reset_counters()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e.process_bgr_batch(bgr, step=1, bound=20, new_size=new_size)
+    torch.cuda.synchronize(dev)
+    dt = shard.all_max(time.perf_counter() - t0, dev)
+    c = e.counters()
+    value = world * args.steps * P / dt
+    if rank == 0:
+        import cv2
+        import multiprocessing as mp
+        # parity of the chain's output: the decoded JPEGs against the quantised planes of the same engine on cv2-prepared frames
+        frames = [cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in bgr[:2]]
+        if new_size:
+            frames = [cv2.resize(f, new_size) for f in frames]
+        qx, qy = e.calc_batch(frames, 1, bound=20)
+        dx = cv2.imdecode(np.frombuffer(out[0][0], np.uint8), cv2.IMREAD_UNCHANGED)
+        # CPU stages, one pair per core
+        cores = usable_cores()
+        jobs = [(bgr[i % (P + 1)], (W, H), qx[0], qy[0], 20) for i in range(cores)]
+        pool = mp.get_context("spawn").Pool(cores)
+        try:
+            pool.map(_cpu_chain_worker, jobs[:cores])
+            res = pool.map(_cpu_chain_worker, jobs)
+        finally:
+            pool.close()
+            pool.join()
+        prep = float(np.mean([r[0] for r in res]))
+        enc = float(np.mean([r[1] for r in res]))
+        line = {"metric": "%s chain pairs/sec: BGR %dx%d -> gray -> %dx%d -> flow -> quantise -> 2 JPEG" % (alg, SW, SH, W, H), "value": value,
+                "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc + " as the flow size; decoded frames %dx%d BGR" % (SW, SH), "algorithm": alg, "pairs_per_step": P, "bound": 20,
+                           "jpeg_quality": 95, "call": "dfb_process_bgr_batch_host"},
+                "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": c["h2d_bytes"] / args.steps, "d2h_bytes_per_step": c["d2h_bytes"] / args.steps},
+                "gpu_launches": int(c["kernel_launches"]),
+                "jpeg_decoded_vs_planes": {"max_abs": int(np.abs(dx.astype(int) - qx[0].astype(int)).max()),
+                                           "mean_abs": float(np.abs(dx.astype(int) - qx[0].astype(int)).mean())},
+                "cpu_stages": {"cvtColor_resize_ms_per_frame": prep * 1e3, "two_imencode_ms_per_pair": enc * 1e3,
+                               "pairs_per_s_all_cores": cores / (prep + enc), "cores": cores,
+                               "note": "cv2 %s, one pair per core (the reference runs these stages on one thread each, include/dense_flow.h:76-80)" % cv2.__version__}}
+        print(json.dumps(line), flush=True)
+    e.release()
+
+
 def main():
     args = parse()
     alg, W, H, seed, desc = WORKLOADS[args.workload]
@@ -384,6 +476,8 @@ def main():
         return run_reference(args, alg, W, H, seed, desc)
     if args.list > 0:
         return run_list_mode(args, alg, W, H, seed, desc)
+    if args.chain:
+        return run_chain_mode(args, alg, W, H, seed, desc)
 
     import numpy as np
     import torch

@@ -201,6 +201,18 @@ class DenseOpticalFlow:
                                                         cap, C.byref(n), C.c_void_p(s)))
         return buf[:n.value].tobytes()
 
+    # -- imread(".jpg") + cvtColor(BGR2GRAY) of an `-if` frame folder on the GPU (nvJPEG decode; not bit-identical to libjpeg-turbo) --
+    def decode_jpeg_gray_device(self, jpeg_bytes, max_width, max_height, device=None):
+        import torch
+        dev = device if device is not None else torch.device("cuda", self.device)
+        buf = np.frombuffer(jpeg_bytes, np.uint8)
+        out = torch.empty((max_height, max_width), dtype=torch.uint8, device=dev)
+        w, h = C.c_int(), C.c_int()
+        s = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._L.dfb_decode_jpeg_gray_device(self._h, buf.ctypes.data, buf.size, out.data_ptr(), max_width, max_width, max_height,
+                                                        C.byref(w), C.byref(h), C.c_void_p(s)))
+        return out[:h.value, :w.value]
+
     # -- gray -> resize -> flow -> quantise -> JPEG for decoded BGR frames (the reference's chain minus decode / file IO) --
     def process_bgr_batch(self, frames_bgr, step=1, bound=20, new_size=None, quality=95):
         """frames_bgr: list of uint8 [H,W,3]; new_size: (w, h) or None.  Returns [(jpg_x bytes, jpg_y bytes)] per pair."""

@@ -41,9 +41,12 @@ struct dfb_handle {
     // resize coefficient tables on the device, rebuilt when the geometry changes
     std::unique_ptr<JpegEncoder> jpeg;  // created on first use
     // scratch of dfb_process_bgr_batch_host (grown on demand)
+    cudaStream_t s_fetch = nullptr;       // bitstream read-back of the BGR chain
+    std::vector<cudaEvent_t> pb_events;   // events of the BGR chain (grown on demand)
     uint8_t *pb_bgr = nullptr, *pb_gray = nullptr, *pb_frames = nullptr, *pb_q = nullptr;
-    float *pb_flows = nullptr;
-    size_t pb_bgr_cap = 0, pb_gray_cap = 0, pb_frames_cap = 0, pb_q_cap = 0, pb_flows_cap = 0;
+    size_t pb_bgr_cap = 0, pb_gray_cap = 0, pb_frames_cap = 0, pb_q_cap = 0;
+    uint8_t *dec_bgr = nullptr;  // BGR scratch of dfb_decode_jpeg_gray_device
+    size_t dec_bgr_cap = 0;
     void *png_scratch = nullptr;  // min/max partials + ticket + bounds of dfb_flow_to_png_image_device
     ResizeTap *d_taps = nullptr;
     int taps_cap = 0, taps_sw = 0, taps_sh = 0, taps_dw = 0, taps_dh = 0;
@@ -67,7 +70,7 @@ int fail(dfb_handle *h, int code, const std::string &msg) {
 // after a failure in the middle of a call no copy into a caller buffer may still be in flight when the call returns
 void quiesce(dfb_handle *h) {
     if (!h) return;
-    for (cudaStream_t s : {h->s_in, h->s_compute, h->s_out})
+    for (cudaStream_t s : {h->s_in, h->s_compute, h->s_out, h->s_fetch})
         if (s) cudaStreamSynchronize(s);
     cudaGetLastError();
 }
@@ -335,10 +338,13 @@ void dfb_destroy(dfb_handle *h) {
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
     h->jpeg.reset();
-    for (void *p : {(void *)h->pb_bgr, (void *)h->pb_gray, (void *)h->pb_frames, (void *)h->pb_q, (void *)h->pb_flows})
+    for (void *p : {(void *)h->pb_bgr, (void *)h->pb_gray, (void *)h->pb_frames, (void *)h->pb_q})
         if (p) cudaFree(p);
     if (h->d_taps) cudaFree(h->d_taps);
     if (h->png_scratch) cudaFree(h->png_scratch);
+    if (h->dec_bgr) cudaFree(h->dec_bgr);
+    for (auto e : h->pb_events) cudaEventDestroy(e);
+    if (h->s_fetch) cudaStreamDestroy(h->s_fetch);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -577,6 +583,36 @@ int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_
     });
 }
 
+int dfb_decode_jpeg_gray_device(dfb_handle *h, const uint8_t *jpeg, size_t jpeg_len, uint8_t *gray, size_t gray_pitch, int max_width,
+                                int max_height, int *width, int *height, void *stream) {
+    if (!h) return DFB_ERR_INVALID_ARG;
+    if (!jpeg || !jpeg_len || !gray || !width || !height) return fail(h, DFB_ERR_INVALID_ARG, "null buffer");
+    return guarded(h, [&]() {
+        DFB_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (!h->jpeg) h->jpeg.reset(new JpegEncoder());
+        int w = 0, hh = 0, nc = 0;
+        h->jpeg->image_info(jpeg, jpeg_len, &w, &hh, &nc);
+        *width = w;
+        *height = hh;
+        if (w <= 0 || hh <= 0) return fail(h, DFB_ERR_INVALID_ARG, "not a JPEG image");
+        if (w > max_width || hh > max_height || gray_pitch < (size_t)w)
+            return fail(h, DFB_ERR_SIZE, "decoded frame " + std::to_string(w) + "x" + std::to_string(hh) + " does not fit the output buffer");
+        const size_t need = (size_t)w * hh * 3;
+        if (need > h->dec_bgr_cap) {
+            DFB_CUDA(cudaDeviceSynchronize());
+            if (h->dec_bgr) DFB_CUDA(cudaFree(h->dec_bgr));
+            DFB_CUDA(cudaMalloc(&h->dec_bgr, need));
+            h->dec_bgr_cap = need;
+        }
+        // imread(IMREAD_COLOR) -> BGR, then the decode stage's cvtColor(BGR2GRAY) (src/denseflow_gpu.cpp:160-163), bit-exact from there on
+        h->jpeg->decode_bgr(jpeg, jpeg_len, h->dec_bgr, (size_t)w * 3, w, hh, s);
+        launch_bgr_to_gray(h->dec_bgr, (size_t)w * 3, w, hh, gray, gray_pitch, s);
+        ++h->alg->launches;
+        return (int)DFB_OK;
+    });
+}
+
 int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_frames, int step, int sw, int sh, int dw, int dh,
                                int bound, int jpeg_quality, uint8_t *const *jpg_x, uint8_t *const *jpg_y, size_t capacity,
                                size_t *len_x, size_t *len_y) {
@@ -597,47 +633,121 @@ int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_f
     return guarded(h, [&]() {
         DFB_CUDA(cudaSetDevice(h->device));
         ensure_host_path(h);
-        cudaStream_t s = h->s_compute;
+        if (!h->s_fetch) DFB_CUDA(cudaStreamCreateWithFlags(&h->s_fetch, cudaStreamNonBlocking));
+        FlowAlgorithm &alg = *h->alg;
+        alg.begin_batch();
         auto grow = [&](auto *&ptr, size_t &cap, size_t need) {
             if (need <= cap) return;
-            DFB_CUDA(cudaStreamSynchronize(s));
+            DFB_CUDA(cudaDeviceSynchronize());
             if (ptr) DFB_CUDA(cudaFree(ptr));
             void *p = nullptr;
             DFB_CUDA(cudaMalloc(&p, need));
             ptr = static_cast<std::remove_reference_t<decltype(ptr)>>(p);
             cap = need;
         };
-        const size_t fpx = (size_t)dw * dh;
-        grow(h->pb_bgr, h->pb_bgr_cap, (size_t)sw * sh * 3);
+        // Three stages on three streams, groups of B pairs in flight (the reference runs the same three stages as three host
+        // threads around queues, include/dense_flow.h:76-80):
+        //   s_in      H2D of BGR frame f -> cvtColor -> resize into the gray frame array        (decode stage tail, :163-170)
+        //   s_compute pyramids / polynomial expansions + flow of group g, quantised planes out   (:313-342 + src/common.cpp:4-16)
+        //   s_out     two JPEG encodes per pair of group g (nvJPEG, one encoder state per plane)  (src/common.cpp:56-57)
+        //   s_fetch   bitstreams of group g-1 to the host while the GPU works on group g
+        const int B = std::max(1, std::min(alg.max_concurrent_pairs(dw, dh), 8));
+        const size_t fpx = (size_t)dw * dh, bgr_bytes = (size_t)sw * sh * 3;
+        grow(h->pb_bgr, h->pb_bgr_cap, 2 * bgr_bytes);           // two staging frames: H2D of f+1 overlaps gray/resize of f
         grow(h->pb_gray, h->pb_gray_cap, (size_t)sw * sh);
         grow(h->pb_frames, h->pb_frames_cap, fpx * n_frames);
-        grow(h->pb_flows, h->pb_flows_cap, fpx * 2 * sizeof(float) * M);
-        grow(h->pb_q, h->pb_q_cap, fpx * 2);
-        // decode stage tail: BGR -> gray -> resize (src/denseflow_gpu.cpp:163-170)
-        for (int f = 0; f < n_frames; ++f) {
-            DFB_CUDA(cudaMemcpyAsync(h->pb_bgr, bgr[f], (size_t)sw * sh * 3, cudaMemcpyHostToDevice, s));
-            h->counters.h2d_bytes += (size_t)sw * sh * 3;
-            uint8_t *dst = h->pb_frames + fpx * f;
-            if (dw == sw && dh == sh) {
-                launch_bgr_to_gray(h->pb_bgr, (size_t)sw * 3, sw, sh, dst, dw, s);
-            } else {
-                launch_bgr_to_gray(h->pb_bgr, (size_t)sw * 3, sw, sh, h->pb_gray, sw, s);
-                const int rc = dfb_resize_gray_device(h, h->pb_gray, sw, sw, sh, dst, dw, dw, dh, s);
-                if (rc != DFB_OK) throw std::runtime_error(h->last_error);
-            }
-            // the staging BGR buffer is reused by the next frame: the H2D of frame f+1 is stream-ordered after this kernel
+        grow(h->pb_q, h->pb_q_cap, fpx * 2 * 2 * B);              // quantised planes of two groups
+        alg.ensure_slots(B + astep + 1);
+        const int nslots = alg.num_slots();
+        while ((int)h->pb_events.size() < n_frames + 8) {
+            cudaEvent_t e;
+            DFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->pb_events.push_back(e);
         }
-        // flow stage (src/denseflow_gpu.cpp:313-342)
-        const int rc = dfb_calc_batch_device(h, h->pb_frames, n_frames, step, dw, dh, h->pb_flows, s);
-        if (rc != DFB_OK) throw std::runtime_error(h->last_error);
-        // encode stage (src/common.cpp:48-64): bound + quantise, then one JPEG per plane
+        cudaEvent_t *ev_frame = h->pb_events.data() + 8;          // [n_frames]
+        cudaEvent_t *ev_gray = h->pb_events.data();                // [2] staging buffer consumed
+        cudaEvent_t *ev_flow = h->pb_events.data() + 2;            // [2] group's planes ready
+        cudaEvent_t *ev_enc = h->pb_events.data() + 4;             // [2] group's encodes done
         if (!h->jpeg) h->jpeg.reset(new JpegEncoder());
-        for (int j = 0; j < M; ++j) {
-            launch_quantise(h->pb_flows + fpx * 2 * j, (size_t)dw * 8, dw, dh, bound, h->pb_q, h->pb_q + fpx, dw, s);
-            len_x[j] = h->jpeg->encode_gray(h->pb_q, dw, dw, dh, jpeg_quality, jpg_x[j], capacity, s);
-            len_y[j] = h->jpeg->encode_gray(h->pb_q + fpx, dw, dw, dh, jpeg_quality, jpg_y[j], capacity, s);
-            h->counters.d2h_bytes += len_x[j] + len_y[j];
+        h->jpeg->ensure_states(4 * B);
+
+        int uploaded = 0;
+        auto upload_until = [&](int last) {
+            for (; uploaded <= std::min(last, n_frames - 1); ++uploaded) {
+                const int f = uploaded, sb = f & 1;
+                if (f >= 2) DFB_CUDA(cudaStreamWaitEvent(h->s_in, ev_gray[sb], 0));
+                uint8_t *stage = h->pb_bgr + (size_t)sb * bgr_bytes;
+                DFB_CUDA(cudaMemcpyAsync(stage, bgr[f], bgr_bytes, cudaMemcpyHostToDevice, h->s_in));
+                h->counters.h2d_bytes += bgr_bytes;
+                uint8_t *dst = h->pb_frames + fpx * f;
+                if (dw == sw && dh == sh) {
+                    launch_bgr_to_gray(stage, (size_t)sw * 3, sw, sh, dst, dw, h->s_in);
+                } else {
+                    launch_bgr_to_gray(stage, (size_t)sw * 3, sw, sh, h->pb_gray, sw, h->s_in);
+                    const int rc = dfb_resize_gray_device(h, h->pb_gray, sw, sw, sh, dst, dw, dw, dh, h->s_in);
+                    if (rc != DFB_OK) throw std::runtime_error(h->last_error);
+                }
+                alg.launches += 1;
+                DFB_CUDA(cudaEventRecord(ev_gray[sb], h->s_in));
+                DFB_CUDA(cudaEventRecord(ev_frame[f], h->s_in));
+            }
+        };
+        int prepared = 0;
+        std::vector<FlowAlgorithm::PairJob> jobs(B);
+        auto flow_group = [&](int g) {
+            const int j0 = g * B, m = std::min(B, M - j0), slot = g & 1;
+            const int last_frame = j0 + m - 1 + astep;
+            upload_until(last_frame + 1);
+            DFB_CUDA(cudaStreamWaitEvent(h->s_compute, ev_frame[last_frame], 0));
+            if (g >= 2) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, ev_enc[slot], 0));  // the planes of group g-2 have been encoded
+            for (; prepared <= last_frame; ++prepared)
+                alg.prepare_frame(h->pb_frames + fpx * prepared, dw, dw, dh, prepared % nslots, h->s_compute);
+            for (int i = 0; i < m; ++i) {
+                const int j = j0 + i;
+                FlowAlgorithm::PairJob &pj = jobs[i];
+                pj = FlowAlgorithm::PairJob{};
+                pj.slot_a = (step > 0 ? j : j + astep) % nslots;  // :315
+                pj.slot_b = (step > 0 ? j + astep : j) % nslots;  // :316
+                pj.bound = bound;
+                pj.qx = h->pb_q + ((size_t)(slot * B + i) * 2) * fpx;
+                pj.qy = pj.qx + fpx;
+                pj.q_pitch = (size_t)dw;
+            }
+            alg.solve_batch(jobs.data(), m, dw, dh, h->s_compute);
+            DFB_CUDA(cudaEventRecord(ev_flow[slot], h->s_compute));
+            // encode stage (src/common.cpp:48-64): one JPEG per plane
+            DFB_CUDA(cudaStreamWaitEvent(h->s_out, ev_flow[slot], 0));
+            for (int i = 0; i < m; ++i) {
+                const uint8_t *qx = h->pb_q + ((size_t)(slot * B + i) * 2) * fpx;
+                h->jpeg->enqueue((slot * B + i) * 2, qx, dw, dw, dh, jpeg_quality, h->s_out);
+                h->jpeg->enqueue((slot * B + i) * 2 + 1, qx + fpx, dw, dw, dh, jpeg_quality, h->s_out);
+            }
+            DFB_CUDA(cudaEventRecord(ev_enc[slot], h->s_out));
+            h->counters.pairs += m;
+        };
+        auto finish_group = [&](int g) {
+            const int j0 = g * B, m = std::min(B, M - j0), slot = g & 1;
+            DFB_CUDA(cudaEventSynchronize(ev_enc[slot]));
+            for (int i = 0; i < m; ++i)
+                for (int c = 0; c < 2; ++c) {
+                    const int st = (slot * B + i) * 2 + c;
+                    const size_t len = h->jpeg->length(st, h->s_fetch);
+                    if (len > capacity) throw std::runtime_error("jpeg output buffer too small (" + std::to_string(len) + " > " + std::to_string(capacity) + ")");
+                    (c ? len_y : len_x)[j0 + i] = len;
+                    h->jpeg->fetch(st, (c ? jpg_y : jpg_x)[j0 + i], len, h->s_fetch);
+                    h->counters.d2h_bytes += len;
+                }
+            DFB_CUDA(cudaStreamSynchronize(h->s_fetch));
+        };
+        const int G = (M + B - 1) / B;
+        for (int g = 0; g < G; ++g) {
+            flow_group(g);
+            if (g > 0) finish_group(g - 1);
         }
+        finish_group(G - 1);
+        DFB_CUDA(cudaStreamSynchronize(h->s_in));
+        DFB_CUDA(cudaStreamSynchronize(h->s_compute));
+        DFB_CUDA(cudaStreamSynchronize(h->s_out));
         return DFB_OK;
     });
 }

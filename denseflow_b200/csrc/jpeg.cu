@@ -7,6 +7,7 @@
 #include <nvjpeg.h>
 
 #include <mutex>
+#include <vector>
 
 #include "jpeg.h"
 
@@ -27,6 +28,10 @@ struct Api {
     decltype(&nvjpegEncoderParamsSetOptimizedHuffman) SetOptHuff = nullptr;
     decltype(&nvjpegEncodeYUV) EncodeYUV = nullptr;
     decltype(&nvjpegEncodeRetrieveBitstream) Retrieve = nullptr;
+    decltype(&nvjpegJpegStateCreate) JpegStateCreate = nullptr;
+    decltype(&nvjpegJpegStateDestroy) JpegStateDestroy = nullptr;
+    decltype(&nvjpegGetImageInfo) GetImageInfo = nullptr;
+    decltype(&nvjpegDecode) Decode = nullptr;
 };
 
 Api &api() {
@@ -50,6 +55,10 @@ Api &api() {
         DFB_SYM(SetOptHuff, nvjpegEncoderParamsSetOptimizedHuffman);
         DFB_SYM(EncodeYUV, nvjpegEncodeYUV);
         DFB_SYM(Retrieve, nvjpegEncodeRetrieveBitstream);
+        DFB_SYM(JpegStateCreate, nvjpegJpegStateCreate);
+        DFB_SYM(JpegStateDestroy, nvjpegJpegStateDestroy);
+        DFB_SYM(GetImageInfo, nvjpegGetImageInfo);
+        DFB_SYM(Decode, nvjpegDecode);
 #undef DFB_SYM
     });
     return a;
@@ -63,30 +72,42 @@ void check(nvjpegStatus_t st, const char *what) {
 
 struct JpegEncoder::Impl {
     nvjpegHandle_t handle = nullptr;
-    nvjpegEncoderState_t state = nullptr;
+    std::vector<nvjpegEncoderState_t> states;
     nvjpegEncoderParams_t params = nullptr;
     int quality = -1;
+    nvjpegJpegState_t dec_state = nullptr;  // created on the first decode
 };
 
 JpegEncoder::JpegEncoder() : impl_(new Impl) {
     Api &a = api();
     if (!a.lib || !a.CreateSimple || !a.EncodeYUV || !a.Retrieve) throw std::runtime_error("nvjpeg: libnvjpeg.so.12 could not be loaded");
     check(a.CreateSimple(&impl_->handle), "nvjpegCreateSimple");
-    check(a.StateCreate(impl_->handle, &impl_->state, nullptr), "nvjpegEncoderStateCreate");
     check(a.ParamsCreate(impl_->handle, &impl_->params, nullptr), "nvjpegEncoderParamsCreate");
+    ensure_states(1);
 }
 
 JpegEncoder::~JpegEncoder() {
     Api &a = api();
     if (impl_->params) a.ParamsDestroy(impl_->params);
-    if (impl_->state) a.StateDestroy(impl_->state);
+    for (auto st : impl_->states)
+        if (st) a.StateDestroy(st);
+    if (impl_->dec_state && a.JpegStateDestroy) a.JpegStateDestroy(impl_->dec_state);
     if (impl_->handle) a.Destroy(impl_->handle);
     delete impl_;
 }
 
-size_t JpegEncoder::encode_gray(const uint8_t *gray, size_t pitch, int w, int h, int quality, uint8_t *out, size_t out_cap,
-                                cudaStream_t s) {
+void JpegEncoder::ensure_states(int n) {
     Api &a = api();
+    while ((int)impl_->states.size() < n) {
+        nvjpegEncoderState_t st = nullptr;
+        check(a.StateCreate(impl_->handle, &st, nullptr), "nvjpegEncoderStateCreate");
+        impl_->states.push_back(st);
+    }
+}
+
+void JpegEncoder::enqueue(int state, const uint8_t *gray, size_t pitch, int w, int h, int quality, cudaStream_t s) {
+    Api &a = api();
+    ensure_states(state + 1);
     if (quality != impl_->quality) {
         check(a.SetQuality(impl_->params, quality, s), "SetQuality");
         check(a.SetSampling(impl_->params, NVJPEG_CSS_GRAY, s), "SetSamplingFactors");
@@ -96,12 +117,49 @@ size_t JpegEncoder::encode_gray(const uint8_t *gray, size_t pitch, int w, int h,
     nvjpegImage_t img{};
     img.channel[0] = const_cast<unsigned char *>(gray);
     img.pitch[0] = pitch;
-    check(a.EncodeYUV(impl_->handle, impl_->state, impl_->params, &img, NVJPEG_CSS_GRAY, w, h, s), "nvjpegEncodeYUV");
+    check(a.EncodeYUV(impl_->handle, impl_->states[state], impl_->params, &img, NVJPEG_CSS_GRAY, w, h, s), "nvjpegEncodeYUV");
+}
+
+size_t JpegEncoder::length(int state, cudaStream_t s) {
     size_t len = 0;
-    check(a.Retrieve(impl_->handle, impl_->state, nullptr, &len, s), "RetrieveBitstream(size)");
+    check(api().Retrieve(impl_->handle, impl_->states.at(state), nullptr, &len, s), "RetrieveBitstream(size)");
+    return len;
+}
+
+void JpegEncoder::fetch(int state, uint8_t *out, size_t len, cudaStream_t s) {
+    check(api().Retrieve(impl_->handle, impl_->states.at(state), out, &len, s), "RetrieveBitstream");
+}
+
+void JpegEncoder::image_info(const uint8_t *jpeg, size_t len, int *w, int *h, int *components) {
+    Api &a = api();
+    if (!a.GetImageInfo) throw std::runtime_error("nvjpeg: decode entry points are missing");
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {}, hs[NVJPEG_MAX_COMPONENT] = {};
+    nvjpegChromaSubsampling_t css;
+    check(a.GetImageInfo(impl_->handle, jpeg, len, &nc, &css, ws, hs), "nvjpegGetImageInfo");
+    *w = ws[0];
+    *h = hs[0];
+    if (components) *components = nc;
+}
+
+void JpegEncoder::decode_bgr(const uint8_t *jpeg, size_t len, uint8_t *bgr, size_t pitch, int w, int h, cudaStream_t s) {
+    Api &a = api();
+    if (!a.Decode || !a.JpegStateCreate) throw std::runtime_error("nvjpeg: decode entry points are missing");
+    if (!impl_->dec_state) check(a.JpegStateCreate(impl_->handle, &impl_->dec_state), "nvjpegJpegStateCreate");
+    (void)w;
+    (void)h;
+    nvjpegImage_t out{};
+    out.channel[0] = bgr;
+    out.pitch[0] = pitch;
+    check(a.Decode(impl_->handle, impl_->dec_state, jpeg, len, NVJPEG_OUTPUT_BGRI, &out, s), "nvjpegDecode");
+}
+
+size_t JpegEncoder::encode_gray(const uint8_t *gray, size_t pitch, int w, int h, int quality, uint8_t *out, size_t out_cap,
+                                cudaStream_t s) {
+    enqueue(0, gray, pitch, w, h, quality, s);
     DFB_CUDA(cudaStreamSynchronize(s));
+    const size_t len = length(0, s);
     if (len > out_cap) throw std::runtime_error("nvjpeg: output buffer too small (" + std::to_string(len) + " > " + std::to_string(out_cap) + ")");
-    check(a.Retrieve(impl_->handle, impl_->state, out, &len, s), "RetrieveBitstream");
+    fetch(0, out, len, s);
     DFB_CUDA(cudaStreamSynchronize(s));
     return len;
 }

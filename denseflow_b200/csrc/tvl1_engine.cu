@@ -54,6 +54,7 @@ class Tvl1 final : public FlowAlgorithm {
         }
         if (stats_event_) cudaEventDestroy(stats_event_);
         if (pair_log_) cudaFreeHost(pair_log_);
+        if (unfused_scratch_) cudaFree(unfused_scratch_);
         for (auto &e : timing_ev_)
             for (auto ev : e)
                 if (ev) cudaEventDestroy(ev);
@@ -199,11 +200,16 @@ class Tvl1 final : public FlowAlgorithm {
         std::memcpy(last_lv_, lv, sizeof(lv));
         if (!prm_.fused) {
             for (int i = 0; i < count; ++i) {
-                if (!jobs[i].flow_xy) throw std::runtime_error("tvl1 (fused = 0): the float2 flow buffer is needed as scratch");
-                solve_unfused(jobs[i].slot_a, jobs[i].slot_b, lv, n, jobs[i].flow_xy, jobs[i].flow_pitch_bytes, s);
+                float *flow = jobs[i].flow_xy;
+                size_t pitch = jobs[i].flow_pitch_bytes;
+                if (!flow) {  // quantised output only: the float2 field lives in an engine-owned scratch plane
+                    if (!unfused_scratch_) DFB_CUDA(cudaMalloc(&unfused_scratch_, (size_t)max_w_ * max_h_ * 2 * sizeof(float)));
+                    flow = unfused_scratch_;
+                    pitch = (size_t)w * 2 * sizeof(float);
+                }
+                solve_unfused(jobs[i].slot_a, jobs[i].slot_b, lv, n, flow, pitch, s);
                 if (jobs[i].bound > 0) {  // the reference's structure: a separate pass over the finished field
-                    launch_quantise(jobs[i].flow_xy, jobs[i].flow_pitch_bytes, lv[0].w, lv[0].h, jobs[i].bound, jobs[i].qx, jobs[i].qy,
-                                    jobs[i].q_pitch, s);
+                    launch_quantise(flow, pitch, lv[0].w, lv[0].h, jobs[i].bound, jobs[i].qx, jobs[i].qy, jobs[i].q_pitch, s);
                     ++launches;
                 }
             }
@@ -551,6 +557,7 @@ class Tvl1 final : public FlowAlgorithm {
         pixel_chunks = 0;
     }
     uint64_t unfused_px_iters_ = 0;
+    float *unfused_scratch_ = nullptr;
 
     static constexpr size_t kMaxPartials = 1 << 16;
 

@@ -149,6 +149,18 @@ int dfb_encode_jpeg_gray_device(dfb_handle *h, const uint8_t *gray, size_t gray_
                                 uint8_t *out, size_t out_capacity, size_t *out_len, void *stream);
 
 /*
+ * Decode one JPEG frame of an `-if` frame folder on the GPU (SURVEY §8 f3 remainder): replaces imread(path) [IMREAD_COLOR]
+ * + cvtColor(BGR2GRAY) of the decode stage (src/denseflow_gpu.cpp:154-163) for JPEG inputs.  jpeg: the file's bytes in host
+ * memory; gray: device buffer of at least max_width x max_height (row pitch in bytes); *width / *height receive the frame size.
+ * nvJPEG decodes to BGR; the gray conversion is the bit-exact kernel of dfb_bgr_to_gray_device.  nvJPEG's IDCT and chroma
+ * upsampling are NOT bit-identical to libjpeg-turbo's (the decoder behind imread): gray frames differ by a level or two
+ * on a few percent of the pixels, which moves the flow by ~1e-2 px AEE at most on the synthetic clips — use it
+ * when throughput matters more than bit-reproducing the reference's decode.  Video files (VideoCapture, :118-151) stay on the host.
+ */
+int dfb_decode_jpeg_gray_device(dfb_handle *h, const uint8_t *jpeg, size_t jpeg_len, uint8_t *gray, size_t gray_pitch, int max_width,
+                                int max_height, int *width, int *height, void *stream);
+
+/*
  * Work counters of the most recent calc on this handle (for the roofline arithmetic):
  *   iters[nscales*warps] executed inner iterations per (scale, warp), index s*warps + w, s = 0 finest
  *   level_w/level_h[nscales] pyramid sizes

@@ -10,9 +10,9 @@ for (W, H) in [(1280, 720), (1920, 1080), (340, 256)]:
     dev = torch.from_numpy(fr).cuda()
     out = torch.empty((N - 1, H, W, 2), dtype=torch.float32, device="cuda")
     ref = None
-    for tma in (0, 1):
+    for tma, tk in ((0, 1), (1, 1), (1, 0)):
         e = d.FarnebackOpticalFlow.create(0, W, H)
-        e.set("use_tma", tma); e.set("time_kernels", 1)
+        e.set("use_tma", tma); e.set("time_kernels", tk)
         for _ in range(2):
             e.calc_batch_device(dev, 1, out)
         torch.cuda.synchronize(); e.reset_counters()
@@ -25,7 +25,8 @@ for (W, H) in [(1280, 720), (1920, 1080), (340, 256)]:
         c = e.counters()
         res = out.cpu().numpy()
         if ref is None: ref = res.copy()
-        kt = c["timed_kernel_ns"] / 1e9 / 3
+        kt = max(c["timed_kernel_ns"], 1) / 1e9 / 3
+        print("time_kernels=%d " % tk, end="")
         print("%dx%d use_tma=%d: %.3f ms/pair (%.1f pairs/s); iteration kernels %.3f ms/pair = %.0f GB/s at 88 B/px.iter; identical to LDG: %s" % (
             W, H, tma, dt / (N - 1) * 1e3, (N - 1) / dt, kt / (N - 1) * 1e3, 88.0 * c["pixel_iters"] / 3 / kt / 1e9, np.array_equal(res, ref)))
         e.release()

@@ -17,4 +17,10 @@ for (w, h) in [(131, 97), (340, 256)]:
     print("farn", w, h, float(np.abs(of).max()), np.isfinite(of).all())
     bgr = torch.from_numpy(np.stack([fr[0]] * 3, -1).copy()).cuda()
     g = e.bgr_to_gray_device(bgr); r = e.resize_gray_device(g, 77, 55); torch.cuda.synchronize()
+    png, bounds = e.flow_to_png_image_device(torch.from_numpy(out[0]).cuda())
+    chain = e.process_bgr_batch([np.stack([x] * 3, -1) for x in fr], step=1, bound=20, new_size=(64, 48))
+    print("png bounds", bounds, "chain jpegs", len(chain), len(chain[0][0]))
+from denseflow_b200 import listrun
+clips = [list(synth.stream(96, 128, n, seed=9 + n)) for n in (5, 1, 7, 3)]
+print("list", listrun.run_list("tvl1", [0, 0], clips, step=1, bound=20, chunk_flows=3)["flows"])
 print("ok")
