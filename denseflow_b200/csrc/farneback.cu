@@ -181,9 +181,10 @@ __global__ void __launch_bounds__(256) k_poly_exp(Plane src, Plane5 R, const Far
 __constant__ float c_border[6] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f, 1.f};
 
 // ---- B.4 updateMatrices ------------------------------------------------------------------------------
-__device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, float dx, float dy, const Plane5 &R0,
-                                                   const Plane5 &R1, float m[5]) {
-    const size_t o = (size_t)y * pitch + x;
+// r0[5]: the five R0 planes at (x, y), loaded by the caller (the iteration kernel fetches them at the start of a tile,
+// long before the flow that the R1 gather depends on exists)
+__device__ __forceinline__ void update_matrices_px_r0(int x, int y, int w, int h, int pitch, float dx, float dy, const float r0[5],
+                                                      const Plane5 &R1, float m[5]) {
     float fx = x + dx, fy = y + dy;
     const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
     fx -= x1;
@@ -197,17 +198,17 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
         r4 = a00 * R1.p[2][j] + a01 * R1.p[2][j + 1] + a10 * R1.p[2][j + pitch] + a11 * R1.p[2][j + pitch + 1];
         r5 = a00 * R1.p[3][j] + a01 * R1.p[3][j + 1] + a10 * R1.p[3][j + pitch] + a11 * R1.p[3][j + pitch + 1];
         r6 = a00 * R1.p[4][j] + a01 * R1.p[4][j + 1] + a10 * R1.p[4][j + pitch] + a11 * R1.p[4][j + pitch + 1];
-        r4 = (R0.p[2][o] + r4) * 0.5f;
-        r5 = (R0.p[3][o] + r5) * 0.5f;
-        r6 = (R0.p[4][o] + r6) * 0.25f;
+        r4 = (r0[2] + r4) * 0.5f;
+        r5 = (r0[3] + r5) * 0.5f;
+        r6 = (r0[4] + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = R0.p[2][o];
-        r5 = R0.p[3][o];
-        r6 = R0.p[4][o] * 0.5f;
+        r4 = r0[2];
+        r5 = r0[3];
+        r6 = r0[4] * 0.5f;
     }
-    r2 = (R0.p[0][o] - r2) * 0.5f;
-    r3 = (R0.p[1][o] - r3) * 0.5f;
+    r2 = (r0[0] - r2) * 0.5f;
+    r3 = (r0[1] - r3) * 0.5f;
     r2 = r2 + (r4 * dy + r6 * dx);
     r3 = r3 + (r6 * dy + r5 * dx);
     const float scale = c_border[min(x, 5)] * c_border[min(y, 5)] * c_border[min(w - x - 1, 5)] * c_border[min(h - y - 1, 5)];
@@ -221,6 +222,13 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     m[2] = r5 * r5 + r6 * r6;
     m[3] = r4 * r2 + r6 * r3;
     m[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, float dx, float dy, const Plane5 &R0,
+                                                   const Plane5 &R1, float m[5]) {
+    const size_t o = (size_t)y * pitch + x;
+    const float r0[5] = {R0.p[0][o], R0.p[1][o], R0.p[2][o], R0.p[3][o], R0.p[4][o]};
+    update_matrices_px_r0(x, y, w, h, pitch, dx, dy, r0, R1, m);
 }
 
 // Several independent pairs per launch (blockIdx.z = pair): the coarse levels are far too small to fill 148 SMs and
@@ -275,13 +283,32 @@ constexpr int kBoxPlaneSlot = ((RW * (BH + 12) + 31) / 32) * 32;  // floats per 
 
 // The part of the iteration that works out of shared memory: raw = the five (BH + 2 HALF) x (BW + 2 HALF) windows of M
 // (index-clamped), vs = scratch for the vertical sums.  Shared by the LDG-staged and the TMA-staged kernel.
-template <int HALF>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// after_vertical() runs once the vertical sums are in `vs` and every thread is done with `raw` (the TMA kernel asks for the
+// next tile's windows there, so they land while this tile's long half — solve, gathers, rebuild — is still running).
+template <int HALF, typename Hook = NoHook>
 __device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPlaneSlot] */, float (*vs)[BH][BW + 2 * HALF], const PairArgs &a, int mb,
-                                                 int rebuild, int x0, int y0, int tid) {
+                                                 int rebuild, int x0, int y0, int tid, Hook after_vertical = Hook()) {
     const Plane5 Mout = a.M[mb ^ 1], R0 = a.R0, R1 = a.R1;
     const Plane fxp = a.fx, fyp = a.fy;
     constexpr int sw = BW + 2 * HALF;
     const int w = Mout.w, h = Mout.h, pitch = Mout.pitch;
+    // this thread's pixels in the second half of the tile: fetch their R0 values now (no dependence on the flow), so the
+    // loads are in flight during the two summation passes
+    constexpr int PXE = BW * BH / 256;
+    const int ety = tid / (BW / PXE), etx0 = (tid % (BW / PXE)) * PXE;
+    float r0pre[PXE][5];
+    if (rebuild) {
+        const int yc0 = min(y0 + ety, h - 1);
+#pragma unroll
+        for (int o = 0; o < PXE; ++o) {
+            const size_t oo = (size_t)yc0 * pitch + min(x0 + etx0 + o, w - 1);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) r0pre[o][k] = R0.p[k][oo];
+        }
+    }
     // vertical sums, register-blocked: one task = 4 vertically consecutive outputs of one column and plane
     // (16 window reads for 4 sums instead of 52); each sum keeps the reference's order (centre, then symmetric
     // pairs outward).  Clamped rows are materialised in the window, which equals clamping the tap's row index.
@@ -292,6 +319,120 @@ __device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPla
         float v[VG + 2 * HALF];
 #pragma unroll
         for (int q = 0; q < VG + 2 * HALF; ++q) v[q] = raw[k * kBoxPlaneSlot + (g * VG + q) * RW + tx + (HX - HALF)];
+#pragma unroll
+        for (int o = 0; o < VG; ++o) {
+            float acc = v[o + HALF];
+#pragma unroll
+            for (int j = 1; j <= HALF; ++j) acc = acc + (v[o + HALF - j] + v[o + HALF + j]);
+            vs[k][g * VG + o][tx] = acc;
+        }
+    }
+    __syncthreads();
+    after_vertical();
+    // horizontal sums + solve + rebuild: each thread owns PX consecutive pixels of one row
+    constexpr float area_inv = 1.f / (float)((1 + 2 * HALF) * (1 + 2 * HALF));
+    constexpr int PX = BW * BH / 256;
+    static_assert(PX == 1 || PX == 2 || PX == 4, "tile must be 256, 512 or 1024 pixels");
+    static_assert((2 * HALF) % PX == 0 && (BW + 2 * HALF) % PX == 0, "vector-aligned rows");
+    {
+        const int ty = tid / (BW / PX), tx0 = (tid % (BW / PX)) * PX;
+        const int y = y0 + ty;
+        float b[PX][5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float v[PX + 2 * HALF];
+            if (PX == 4) {
+#pragma unroll
+                for (int q = 0; q < (PX + 2 * HALF) / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(&vs[k][ty][tx0 + 4 * q]);
+                    v[4 * q] = t.x;
+                    v[4 * q + 1] = t.y;
+                    v[4 * q + 2] = t.z;
+                    v[4 * q + 3] = t.w;
+                }
+            } else if (PX == 2) {
+#pragma unroll
+                for (int q = 0; q < (PX + 2 * HALF) / 2; ++q) {
+                    const float2 t = *reinterpret_cast<const float2 *>(&vs[k][ty][tx0 + 2 * q]);
+                    v[2 * q] = t.x;
+                    v[2 * q + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PX + 2 * HALF; ++q) v[q] = vs[k][ty][tx0 + q];
+            }
+#pragma unroll
+            for (int o = 0; o < PX; ++o) {
+                float acc = v[o + HALF];
+#pragma unroll
+                for (int j = 1; j <= HALF; ++j) acc = acc + (v[o + HALF - j] + v[o + HALF + j]);
+                b[o][k] = acc * area_inv;
+            }
+        }
+        // all pixels' gathers are issued before any of them is consumed: coordinates are clamped into the image
+        // (safe reads), only the stores are predicated
+        const int yc = min(y, h - 1);
+        float nfx[PX], nfy[PX], m[PX][5];
+#pragma unroll
+        for (int o = 0; o < PX; ++o) {
+            // updateFlow: g11 = b0, g12 = b1, g22 = b2, h1 = b3, h2 = b4
+            const float det_inv = f_rcp(b[o][0] * b[o][2] - b[o][1] * b[o][1] + 1e-3f);
+            nfx[o] = (b[o][0] * b[o][4] - b[o][1] * b[o][3]) * det_inv;
+            nfy[o] = (b[o][2] * b[o][3] - b[o][1] * b[o][4]) * det_inv;
+        }
+        if (rebuild) {
+#pragma unroll
+            for (int o = 0; o < PX; ++o) update_matrices_px_r0(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], r0pre[o], R1, m[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < PX; ++o) {
+            const int x = x0 + tx0 + o;
+            if (x < w && y < h) {
+                const size_t oo = (size_t)y * pitch + x;
+                fxp.p[oo] = nfx[o];
+                fyp.p[oo] = nfy[o];
+                if (rebuild) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) Mout.p[k][oo] = m[o][k];
+                }
+            }
+        }
+    }
+}
+
+// LDG-staged variant, self-contained (round-1 kernel): one CTA per 32 x 16 tile, window staged with index-clamped scalar loads,
+// 44-float window rows.  Kept as the comparison / fallback path (use_tma = 0); bit-identical to the TMA kernel below.
+template <int HALF>
+__global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
+    const PairArgs &a = args.p[blockIdx.z];
+    const Plane5 Min = a.M[mb], Mout = a.M[mb ^ 1], R0 = a.R0, R1 = a.R1;
+    const Plane fxp = a.fx, fyp = a.fy;
+    constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
+    extern __shared__ float box_smem[];
+    float(*raw)[sh][sw] = reinterpret_cast<float(*)[sh][sw]>(box_smem);               // [5][sh][sw]
+    float(*vs)[BH][sw] = reinterpret_cast<float(*)[BH][sw]>(box_smem + 5 * sh * sw);  // [5][BH][sw]
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    const int w = Min.w, h = Min.h, pitch = Min.pitch;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < sh * sw; i += 256) {
+        const int ty = i / sw, tx = i - ty * sw;
+        const int y = max(0, min(y0 + ty - HALF, h - 1));
+        const int x = max(0, min(x0 + tx - HALF, w - 1));
+        const size_t o = (size_t)y * pitch + x;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) raw[k][ty][tx] = Min.p[k][o];
+    }
+    __syncthreads();
+    // vertical sums, register-blocked: one task = 4 vertically consecutive outputs of one column and plane
+    // (16 window reads for 4 sums instead of 52); each sum keeps the reference's order (centre, then symmetric
+    // pairs outward).  Clamped rows are materialised in the window, which equals clamping the tap's row index.
+    constexpr int VG = 4;
+    for (int i = tid; i < 5 * (BH / VG) * sw; i += 256) {
+        const int tx = i % sw, rest = i / sw;
+        const int g = rest % (BH / VG), k = rest / (BH / VG);
+        float v[VG + 2 * HALF];
+#pragma unroll
+        for (int q = 0; q < VG + 2 * HALF; ++q) v[q] = raw[k][g * VG + q][tx];
 #pragma unroll
         for (int o = 0; o < VG; ++o) {
             float acc = v[o + HALF];
@@ -371,71 +512,45 @@ __device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPla
         }
     }
 }
-
-template <int HALF>
-__global__ void __launch_bounds__(256) k_box_solve_update(const __grid_constant__ FarnBatchArgs args, int mb, int rebuild) {
-    const PairArgs &a = args.p[blockIdx.z];
-    const Plane5 Min = a.M[mb];
-    constexpr int sw = BW + 2 * HALF, sh = BH + 2 * HALF;
-    static_assert(RW * sh <= kBoxPlaneSlot && HX >= HALF, "window fits its slot");
-    extern __shared__ float box_smem[];
-    float *raw = box_smem;                                                                    // [5][kBoxPlaneSlot]
-    float(*vs)[BH][sw] = reinterpret_cast<float(*)[BH][sw]>(box_smem + 5 * kBoxPlaneSlot);  // [5][BH][sw]
-    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
-    const int w = Min.w, h = Min.h, pitch = Min.pitch;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < sh * RW; i += 256) {
-        const int ty = i / RW, tx = i - ty * RW;
-        const int y = max(0, min(y0 + ty - HALF, h - 1));
-        const int x = max(0, min(x0 + tx - HX, w - 1));
-        const size_t o = (size_t)y * pitch + x;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) raw[k * kBoxPlaneSlot + i] = Min.p[k][o];
-    }
-    __syncthreads();
-    box_tile_compute<HALF>(raw, vs, a, mb, rebuild, x0, y0, tid);
-}
-
-// The same iteration as a persistent kernel with TMA-staged, double-buffered windows (the default): a CTA walks the tile
-// list of the whole batch (pairs x tile rows x tile columns); while it sums / solves tile i out of one shared-memory
-// stage, one thread has already asked the TMA unit for the five windows of tile i + 1 (cp.async.bulk.tensor.2d, completion
-// on an mbarrier, zero fill outside the image).  Index-clamped borders: tiles that touch the image border copy the
-// nearest in-image entry of the window into the zero-filled ones (border tiles only), which reproduces the clamped
-// reads of the LDG kernel bit for bit.
+// The same iteration as a persistent kernel with TMA-staged windows (the default): a CTA walks the tile list of the whole
+// batch (pairs x tile rows x tile columns).  The five windows of a tile arrive by cp.async.bulk.tensor.2d (completion on an
+// mbarrier, zero fill outside the image).  The staging buffer is free again as soon as the vertical sums are done, so the
+// request for the NEXT tile's windows goes out there and the copy runs under this tile's long half (solve, the R1 gathers,
+// rebuild of M): one buffer, 41 KB of shared memory, five CTAs per SM like the LDG kernel — and no exposed staging loop.
+// Index-clamped borders: tiles that touch the image border copy the nearest in-image entry of the window into the
+// zero-filled ones (border tiles only), which reproduces the clamped reads of the LDG kernel bit for bit.
 template <int HALF>
 struct BoxTmaSmem {
-    float raw[2][5][kBoxPlaneSlot];
+    float raw[5][kBoxPlaneSlot];
     float vs[5][BH][BW + 2 * HALF];
-    unsigned long long bar[2];
+    unsigned long long bar;
 };
 
+#ifndef DFB_FARN_TMA_MINB
+#define DFB_FARN_TMA_MINB 4
+#endif
 template <int HALF>
-__global__ void __launch_bounds__(256) k_box_solve_update_tma(const __grid_constant__ FarnBatchArgs args, const char *maps, int nb, int ntx, int nty,
-                                                              int mb, int rebuild) {
+__global__ void __launch_bounds__(256, DFB_FARN_TMA_MINB) k_box_solve_update_tma(const __grid_constant__ FarnBatchArgs args, const char *maps, int nb, int ntx, int nty,
+                                                                 int mb, int rebuild) {
     constexpr int sh = BH + 2 * HALF;
     static_assert(RW * sh <= kBoxPlaneSlot && (RW * 4) % 16 == 0 && HX >= HALF, "window fits its slot, rows are 16-byte multiples");
     extern __shared__ __align__(128) unsigned char box_tma_smem[];
     BoxTmaSmem<HALF> &sm = *reinterpret_cast<BoxTmaSmem<HALF> *>(box_tma_smem);
     const int tid = threadIdx.x;
     const int per = ntx * nty, total = nb * per;
-    if (tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
-    }
+    if (tid == 0) mbar_init(&sm.bar, 1);
     __syncthreads();
-    auto issue = [&](int t, int stage) {  // thread 0: the five windows of tile t -> stage
+    auto issue = [&](int t) {  // thread 0: the five windows of tile t
         const int z = t / per, r = t - z * per, ty = r / ntx, tx = r - ty * ntx;
         const char *m = maps + (size_t)((z * 2 + mb) * 5) * kTensorMapBytes;
-        mbar_expect_tx(&sm.bar[stage], 5u * RW * sh * (unsigned)sizeof(float));
+        mbar_expect_tx(&sm.bar, 5u * RW * sh * (unsigned)sizeof(float));
 #pragma unroll
-        for (int k = 0; k < 5; ++k) tma_load_2d(sm.raw[stage][k], m + k * kTensorMapBytes, tx * BW - HX, ty * BH - HALF, &sm.bar[stage]);
+        for (int k = 0; k < 5; ++k) tma_load_2d(sm.raw[k], m + k * kTensorMapBytes, tx * BW - HX, ty * BH - HALF, &sm.bar);
     };
     int t = blockIdx.x;
-    if (t < total && tid == 0) issue(t, 0);
+    if (t < total && tid == 0) issue(t);
     for (int i = 0; t < total; ++i, t += gridDim.x) {
-        const int stage = i & 1;
-        if (t + (int)gridDim.x < total && tid == 0) issue(t + gridDim.x, stage ^ 1);  // every reader of that stage passed the barrier below
-        mbar_wait(&sm.bar[stage], (i >> 1) & 1);
+        mbar_wait(&sm.bar, i & 1);
         const int z = t / per, r = t - z * per, tyi = r / ntx, txi = r - tyi * ntx;
         const PairArgs &a = args.p[z];
         const int x0 = txi * BW, y0 = tyi * BH;
@@ -448,14 +563,20 @@ __global__ void __launch_bounds__(256) k_box_solve_update_tma(const __grid_const
                 if (cy != gy || cx != gx) {
                     const int src = (cy - y0 + HALF) * RW + (cx - x0 + HX);  // an in-image entry: never written by this loop
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) sm.raw[stage][k][j] = sm.raw[stage][k][src];
+                    for (int k = 0; k < 5; ++k) sm.raw[k][j] = sm.raw[k][src];
                 }
             }
             __syncthreads();
         }
-        box_tile_compute<HALF>(&sm.raw[stage][0][0], sm.vs, a, mb, rebuild, x0, y0, tid);
-        fence_proxy_async();  // this thread's reads of the stage are ordered before the TMA writes a later iteration asks for
-        __syncthreads();
+        const int tn = t + (int)gridDim.x;
+        box_tile_compute<HALF>(&sm.raw[0][0], sm.vs, a, mb, rebuild, x0, y0, tid, [&]() {
+            // every thread has passed the barrier behind the vertical sums: the staging buffer is dead
+            if (tn < total && tid == 0) {
+                fence_proxy_async();
+                issue(tn);
+            }
+        });
+        __syncthreads();  // vs is rewritten by the next tile's vertical sums
     }
 }
 
@@ -504,7 +625,7 @@ __global__ void __launch_bounds__(256) k_farn_merge(const __grid_constant__ Farn
     row[x] = make_float2(u, v);
 }
 
-constexpr size_t kBoxSmemBytes = (size_t)(5 * kBoxPlaneSlot + 5 * BH * (BW + 12)) * sizeof(float);
+constexpr size_t kBoxSmemBytes = (size_t)(5 * (BH + 12) * (BW + 12) + 5 * BH * (BW + 12)) * sizeof(float);
 
 struct FarnParams {
     int num_levels = 5;

@@ -150,8 +150,8 @@ __device__ __forceinline__ void phase_warp(const int G, const int bid, const Fus
         const int y2 = has2 ? i2 / W : y, x2 = has2 ? i2 - y2 * W : x;
         const size_t o = (size_t)y * P + x, o2 = (size_t)y2 * P + x2;
         float ix, iy, g, rc, jx, jy, g2, rc2;
-        tvl1_warp_px(I1, I1x, I1y, W, H, P, x, y, u1[o], u2[o], __ldg(L.I0 + o), ix, iy, g, rc);
-        tvl1_warp_px(I1, I1x, I1y, W, H, P, x2, y2, u1[o2], u2[o2], __ldg(L.I0 + o2), jx, jy, g2, rc2);
+        tvl1_warp_px_window(I1, I1x, I1y, W, H, P, x, y, u1[o], u2[o], __ldg(L.I0 + o), ix, iy, g, rc);
+        tvl1_warp_px_window(I1, I1x, I1y, W, H, P, x2, y2, u1[o2], u2[o2], __ldg(L.I0 + o2), jx, jy, g2, rc2);
         job.I1wx[o] = ix;
         job.I1wy[o] = iy;
         job.grad[o] = tvl1_gq_from_grad(g);  // what the primal step wants of the gradient (tvl1_math.cuh)

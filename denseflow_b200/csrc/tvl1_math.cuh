@@ -232,4 +232,50 @@ __device__ __forceinline__ void tvl1_warp_px(const float *__restrict__ I1, const
     rho_c = I1wv - ix * u1v - iy * u2v - I0v;
 }
 
+// The same warp for the persistent kernel: when the 6 x 6 neighbourhood of the 4 x 4 tap window lies inside the image (all
+// but a thin border), I1x / I1y at the taps are recomputed from the I1 values themselves — 0.5f * (I1(x+1) - I1(x-1)) is exactly
+// what the gradient plane holds — so the pixel costs 32 gathers instead of 48 (the phase is latency-bound).  Border pixels,
+// where the gradient is taken at a CLAMPED tap coordinate, take the plane path above.  Bit-identical to tvl1_warp_px.
+__device__ __forceinline__ void tvl1_warp_px_window(const float *__restrict__ I1, const float *I1x, const float *I1y, int W, int H, int P,
+                                                    int x, int y, float u1v, float u2v, float I0v, float &ix, float &iy, float &grad,
+                                                    float &rho_c) {
+    const float wx = x + u1v, wy = y + u2v;
+    const int xmin = (int)ceilf(wx - 2.0f), ymin = (int)ceilf(wy - 2.0f);
+    if (xmin < 1 || ymin < 1 || xmin + 4 > W - 1 || ymin + 4 > H - 1) {
+        tvl1_warp_px(I1, I1x, I1y, W, H, P, x, y, u1v, u2v, I0v, ix, iy, grad, rho_c);
+        return;
+    }
+    float kx[4], ky[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        kx[t] = bicubic_coeff(wx - (float)(xmin + t));
+        ky[t] = bicubic_coeff(wy - (float)(ymin + t));
+    }
+    const float *base = I1 + (size_t)(ymin - 1) * P + (xmin - 1);
+    float v[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            if ((r >= 1 && r <= 4) || (c >= 1 && c <= 4)) v[r][c] = __ldg(base + (size_t)r * P + c);
+    float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float wgt = kx[b] * ky[a];
+            sum = sum + wgt * v[a + 1][b + 1];
+            sumx = sumx + wgt * (0.5f * (v[a + 1][b + 2] - v[a + 1][b]));
+            sumy = sumy + wgt * (0.5f * (v[a + 2][b + 1] - v[a][b + 1]));
+            wsum = wsum + wgt;
+        }
+    }
+    const float coeff = f_rcp(wsum);
+    const float I1wv = sum * coeff;
+    ix = sumx * coeff;
+    iy = sumy * coeff;
+    grad = ix * ix + iy * iy;
+    rho_c = I1wv - ix * u1v - iy * u2v - I0v;
+}
+
 }  // namespace dfb
