@@ -43,6 +43,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, in
                  "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
                  : "memory");
 }
+// Asks the TMA unit to bring a tile into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void *tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // generic-proxy accesses to shared memory before this fence are ordered before later async-proxy (TMA) writes to it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif

@@ -35,6 +35,7 @@ struct Tvl1Params {
     int flag_sync = 1;
     int time_kernels = 0;
     int use_tma = 1;
+    int prefetch = 1;
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
 };
 
@@ -93,6 +94,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "flag_sync") prm_.flag_sync = (int)v;  // 0 CTA barriers, 1 spin on neighbour flags, n > 1: spin with n ns back-off
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "use_tma") prm_.use_tma = v != 0;
+        else if (k == "prefetch") prm_.prefetch = v != 0;
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -111,6 +113,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "flag_sync") *v = prm_.flag_sync;
         else if (k == "time_kernels") *v = prm_.time_kernels;
         else if (k == "use_tma") *v = prm_.use_tma;
+        else if (k == "prefetch") *v = prm_.prefetch;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -455,6 +458,7 @@ class Tvl1 final : public FlowAlgorithm {
             job.k = prm_.fused_k;
             job.flag_sync = prm_.flag_sync;
             job.use_tma = prm_.use_tma;
+            job.prefetch = prm_.prefetch;
             if (prm_.use_tma) ensure_tensor_maps(wk, lv, n);
             job.tmaps = wk.tmaps;
             job.c = Tvl1Consts{(float)(prm_.lambda * prm_.theta), (float)(prm_.tau / prm_.theta), (float)prm_.theta};

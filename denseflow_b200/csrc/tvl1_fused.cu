@@ -377,7 +377,7 @@ __device__ __forceinline__ float tile_iterations(Smem &sm, const TileCtx &t, con
 
 __device__ __forceinline__ float process_tile(const FusedJob &job, const Tvl1Consts &c, const FusedLevel &L, int level, int cur, int tx, int ty,
                                               int kk, int hx, int hy, bool check, int base, unsigned tma_parity, Smem &sm,
-                                              bool prof_on) {
+                                              bool prof_on, int ntx_next, int nty_next) {
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     unsigned long long t0 = 0;
     if (prof_on) t0 = gtime();
@@ -437,6 +437,34 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const Tvl1Con
         }
     }
     if (use_tma) mbar_wait(&sm.tma_bar, tma_parity);
+    if (job.prefetch && ntx_next >= 0) {
+        // This CTA's next tile of the chunk: ask for its ten planes to be brought into L2 now, so the copy from HBM runs
+        // under this tile's iterations (with several pairs in flight the planes of a level do not fit the L2).
+        const int nrx0 = ntx_next * (TW - 2 * hx), nry0 = nty_next * (TH - 2 * hy);
+        if (use_tma && threadIdx.x == 0) {
+            const char *maps = static_cast<const char *>(job.tmaps) + (size_t)level * kFusedMapsPerLevel * kTensorMapBytes;
+            tma_prefetch_l2_2d(maps + 0 * kTensorMapBytes, nrx0, nry0);
+            tma_prefetch_l2_2d(maps + 1 * kTensorMapBytes, nrx0, nry0);
+            tma_prefetch_l2_2d(maps + 2 * kTensorMapBytes, nrx0, nry0);
+            tma_prefetch_l2_2d(maps + 3 * kTensorMapBytes, nrx0, nry0);
+            tma_prefetch_l2_2d(maps + (4 + 2 * cur) * kTensorMapBytes, nrx0, nry0);
+            tma_prefetch_l2_2d(maps + (5 + 2 * cur) * kTensorMapBytes, nrx0, nry0);
+        }
+        if ((lane & 7) == 0) {  // one lane per 128-byte line of the four dual planes
+            const int ngx = nrx0 + 4 * lane;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int ngy = nry0 + RPT * wq + r;
+                if (ngx < P && ngy < H) {
+                    const size_t o = (size_t)ngy * P + ngx;
+                    prefetch_l2(job.p[cur][0] + o);
+                    prefetch_l2(job.p[cur][1] + o);
+                    prefetch_l2(job.p[cur][2] + o);
+                    prefetch_l2(job.p[cur][3] + o);
+                }
+            }
+        }
+    }
     TileCtx t;
     t.so0 = so0;
     t.lane = lane;
@@ -597,7 +625,9 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                     const int ntiles = ntx * nty;
                     for (int t = bid; t < ntiles; t += G) {
                         const int ty = t / ntx, tx = t - ty * ntx;
-                        const float e = process_tile(job, c, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on);
+                        const int tn = t + G;
+                        const int nty_n = tn < ntiles ? tn / ntx : -1, ntx_n = tn < ntiles ? tn - nty_n * ntx : -1;
+                        const float e = process_tile(job, c, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on, ntx_n, nty_n);
                         tile_base += 2 * kk + 2;
                         tma_parity ^= 1u;
                         if (chk) {

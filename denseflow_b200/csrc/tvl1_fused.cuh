@@ -30,6 +30,7 @@ struct FusedJob {
     int nscales, warps, iterations, k;
     int flag_sync;  // 1: neighbour-warp progress counters in the tile loop, 0: CTA-wide barriers
     int use_tma;    // 1: constants + u tiles staged by TMA (cp.async.bulk.tensor.2d), 0: LDG -> STS
+    int prefetch;   // 1: while a tile iterates, the CTA's next tile of the chunk is prefetched into L2 (TMA prefetch + prefetch.global.L2)
     // CUtensorMap[nscales][kFusedMapsPerLevel] in global memory: I1wx, I1wy, grad, rho_c, u1[0], u2[0], u1[1], u2[1]
     const void *tmaps;
     double epsilon;
