@@ -592,6 +592,11 @@ def main():
         b_alg = 88.0 * c["pixel_iters"]
         achieved = b_alg / kt / 1e9
         t = ncu_traffic(args.workload, min(8, P))  # pairs per launch = the engine's batch of up to 8 pairs (blockIdx.z)
+        if t[0] is not None:
+            # the capture is of a FULL-RESOLUTION launch (649 MB algorithmic for 8 pairs at 1280x720); the run's launches cover all
+            # pyramid levels, so the measured bytes are scaled by the algorithmic bytes of an average launch over those of the captured one
+            full = 88.0 * min(8, P) * W * H
+            t = (t[0] * (b_alg / nl) / full, t[1] + "; a full-resolution launch, scaled by %.3f to the run's average launch over all levels" % ((b_alg / nl) / full))
         roof = {"bound": "hbm", "kernel": "k_box_solve_update<6> (13x13 box mean of M -> 2x2 solve -> rebuild M, one launch per iteration and level, up to 8 pairs per launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": t[0], "traffic_source": t[1],
                 "peak_source": peak_src,
