@@ -527,20 +527,6 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const Tvl1Con
 // only matters when the image continues beyond the region
 __host__ __device__ __forceinline__ int tiles_along(int n, int T, int h) { return fused_tiles_along(n, T, h); }
 
-__device__ __forceinline__ double block_sum(double v, Smem &sm) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < kWarps; ++k) s += sm.red[k];
-    }
-    __syncthreads();
-    return s;  // valid in thread 0
-}
-
 // phase profiler (CTA 0 / thread 0 only): attributes wall time between marks to a category
 struct Prof {
     unsigned long long *acc;  // shared memory
@@ -579,7 +565,10 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
     unsigned tma_parity = 0;
     Prof prof;
     prof.init(sm.prof, bid == 0);
-    if (threadIdx.x < kWarps) sm.prog[threadIdx.x] = 0;
+    if (threadIdx.x < kWarps) {
+        sm.prog[threadIdx.x] = 0;
+        sm.red[threadIdx.x] = 0.0;
+    }
     if (threadIdx.x == 0) mbar_init(&sm.tma_bar, 1);
     __syncthreads();
 
@@ -615,7 +604,6 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                     if (nn >= job.iterations) break;
                 }
                 int remaining = K;
-                double cta_err = 0.0;
                 while (remaining > 0) {
                     const int nch = (remaining + job.k - 1) / job.k;
                     const int kk = (remaining + nch - 1) / nch;
@@ -630,12 +618,25 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                         const float e = process_tile(job, c, L, s, cur, tx, ty, kk, hx, hy, chk, tile_base, tma_parity, sm, prof.on, ntx_n, nty_n);
                         tile_base += 2 * kk + 2;
                         tma_parity ^= 1u;
-                        if (chk) {
-                            const double bs = block_sum((double)e, sm);
-                            if (threadIdx.x == 0) cta_err += bs;
+                        if (chk) {  // per-warp running sums in shared memory: no CTA-wide barrier per tile
+                            double v = (double)e;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] += v;
                         }
                     }
-                    if (chk && threadIdx.x == 0) job.partials[bid] = cta_err;
+                    if (chk) {  // one barrier per checking chunk: thread 0 adds the 16 warp sums in a fixed order
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            double bs = 0.0;
+#pragma unroll
+                            for (int k = 0; k < kWarps; ++k) {
+                                bs += sm.red[k];
+                                sm.red[k] = 0.0;
+                            }
+                            job.partials[bid] = bs;
+                        }
+                    }
                     prof.mark(2, 8 + s);
                     if (prof.on) prof.acc[16 + s] += 1;
                     px_chunks += (unsigned long long)(L.w * L.h);
