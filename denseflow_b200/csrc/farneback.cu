@@ -300,8 +300,8 @@ __device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPla
     constexpr int PXE = BW * BH / 256;
     const int ety = tid / (BW / PXE), etx0 = (tid % (BW / PXE)) * PXE;
     float r0pre[PXE][5];
+    const int yc0 = min(y0 + ety, h - 1);
     if (rebuild) {
-        const int yc0 = min(y0 + ety, h - 1);
 #pragma unroll
         for (int o = 0; o < PXE; ++o) {
             const size_t oo = (size_t)yc0 * pitch + min(x0 + etx0 + o, w - 1);
