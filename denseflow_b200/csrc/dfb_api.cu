@@ -28,7 +28,8 @@ struct dfb_handle {
     // host-path plumbing: three streams so H2D of frame i+1, compute of pair i and D2H of flow i-1 overlap
     cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
     static constexpr int kFrameRing = 16; // device u8 frames (dead as soon as their pyramid is built)
-    static constexpr int kFlowRing = 32;  // device flow / quantised outputs (two launches of up to 16 pairs in flight)
+    static constexpr int kFlowRing = 128; // device flow / quantised outputs: two launches of up to 64 pairs in flight; slots are
+                                          // allocated on first use and a call cycles through 2 x (pairs per launch) of them
     uint8_t *d_frame[kFrameRing] = {};
     size_t d_frame_pitch = 0;
     float *d_flow[kFlowRing] = {};
@@ -137,12 +138,21 @@ void ensure_host_path(dfb_handle *h) {
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         DFB_CUDA(cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < dfb_handle::kFlowRing; ++i) {
-        DFB_CUDA(cudaMalloc(&h->d_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float)));
-        DFB_CUDA(cudaMalloc(&h->d_qx[i], (size_t)h->max_w * h->max_h));
-        DFB_CUDA(cudaMalloc(&h->d_qy[i], (size_t)h->max_w * h->max_h));
-        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-        DFB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+}
+
+// output ring slots [0, n): allocated on first use (a 1080p handle runs 7 pairs per launch and touches 14 slots, a 340x256
+// one up to 64 pairs per launch)
+void ensure_flow_ring(dfb_handle *h, int n, bool quantised) {
+    for (int i = 0; i < n; ++i) {
+        if (!h->ev_done[i]) {
+            DFB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            DFB_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+        if (!quantised && !h->d_flow[i]) DFB_CUDA(cudaMalloc(&h->d_flow[i], (size_t)h->max_w * h->max_h * 2 * sizeof(float)));
+        if (quantised && !h->d_qx[i]) {
+            DFB_CUDA(cudaMalloc(&h->d_qx[i], (size_t)h->max_w * h->max_h));
+            DFB_CUDA(cudaMalloc(&h->d_qy[i], (size_t)h->max_w * h->max_h));
+        }
     }
 }
 
@@ -172,7 +182,12 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
     alg.ensure_slots(B + astep + 1);
     const int nslots = alg.num_slots();
     const size_t fbytes = (size_t)w * hh;
-    constexpr int FR = dfb_handle::kFrameRing, OR = dfb_handle::kFlowRing;
+    constexpr int FR = dfb_handle::kFrameRing;
+    const int OR = 2 * B;  // two groups of pairs in flight
+    // the unfused tvl1 schedule needs the float2 field as scratch even when only the quantised planes are wanted
+    ensure_flow_ring(h, OR, bound > 0);
+    double fused_flag = 1;
+    if (bound > 0 && alg.get_param("fused", &fused_flag) && fused_flag == 0) ensure_flow_ring(h, OR, false);
 
     int uploaded = 0;  // frames [0, uploaded) have H2D + pyramid enqueued
     auto upload_until = [&](int last) {
@@ -226,7 +241,7 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
             pj = FlowAlgorithm::PairJob{};
             pj.slot_a = a % nslots;
             pj.slot_b = b % nslots;
-            pj.flow_xy = h->d_flow[ring];
+            pj.flow_xy = h->d_flow[ring];  // null in quantised mode unless the engine needs the scratch (see above)
             pj.flow_pitch_bytes = (size_t)w * 2 * sizeof(float);
             if (bound > 0) {  // f1: the engine's merge epilogue writes the two uint8 planes directly
                 pj.bound = bound;

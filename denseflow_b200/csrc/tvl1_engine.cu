@@ -56,6 +56,11 @@ class Tvl1 final : public FlowAlgorithm {
         if (stats_event_) cudaEventDestroy(stats_event_);
         if (pair_log_) cudaFreeHost(pair_log_);
         if (unfused_scratch_) cudaFree(unfused_scratch_);
+        for (int r = 0; r < kJobRing; ++r) {
+            if (job_ring_h_[r]) cudaFreeHost(job_ring_h_[r]);
+            if (job_ring_d_[r]) cudaFree(job_ring_d_[r]);
+            if (job_ring_ev_[r]) cudaEventDestroy(job_ring_ev_[r]);
+        }
         for (auto &e : timing_ev_)
             for (auto ev : e)
                 if (ev) cudaEventDestroy(ev);
@@ -176,7 +181,10 @@ class Tvl1 final : public FlowAlgorithm {
         const int hy = prm_.fused_k, hx = (hy + 3) & ~3;
         int best = 1;
         double best_u = -1;
-        for (int B = 1; B <= kFusedMaxLanes; ++B) {
+        // lanes are sized for the handle's MAXIMUM frame: keep their total workspace under 8 GB
+        const size_t lane_bytes = 4 * Slab::padded(pyr_elems_, 4) + 14 * Slab::padded(plane_elems_, 4);
+        const int mem_cap = (int)std::max<size_t>(1, (size_t(8) << 30) / std::max<size_t>(lane_bytes, 1));
+        for (int B = 1; B <= std::min(kFusedMaxLanes, mem_cap); ++B) {
             const int G = sms / B;
             if (G < 1) break;
             double num = 0, den = 0;
@@ -448,9 +456,21 @@ class Tvl1 final : public FlowAlgorithm {
         FusedBatch batch{};
         batch.njobs = count;
         batch.group = std::max(1, fused_cta_slots(device_) / count);
+        // job descriptions: filled in a pinned host slot of a small ring, copied to its device twin on the launch stream
+        if (!job_ring_h_[0]) {
+            for (int r = 0; r < kJobRing; ++r) {
+                DFB_CUDA(cudaHostAlloc(&job_ring_h_[r], sizeof(FusedJob) * kFusedMaxLanes, cudaHostAllocDefault));
+                DFB_CUDA(cudaMalloc(&job_ring_d_[r], sizeof(FusedJob) * kFusedMaxLanes));
+                DFB_CUDA(cudaEventCreateWithFlags(&job_ring_ev_[r], cudaEventDisableTiming));
+            }
+        }
+        const int jr = job_ring_next_++ % kJobRing;
+        if (job_ring_next_ > kJobRing) DFB_CUDA(cudaEventSynchronize(job_ring_ev_[jr]));  // the copy out of this host slot has run (no-op if never recorded)
+        FusedJob *host_jobs = job_ring_h_[jr];
         for (int i = 0; i < count; ++i) {
             Lane &wk = lanes_[i];
-            FusedJob &job = batch.job[i];
+            FusedJob &job = host_jobs[i];
+            job = FusedJob{};
             job.nscales = n;
             job.warps = prm_.warps;
             job.iterations = prm_.iterations;
@@ -511,6 +531,12 @@ class Tvl1 final : public FlowAlgorithm {
                 }
             DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][0], s));
         }
+        if (count > kFusedParamLanes) {  // too many for the parameter bank: through the device-memory ring
+            DFB_CUDA(cudaMemcpyAsync(job_ring_d_[jr], host_jobs, sizeof(FusedJob) * count, cudaMemcpyHostToDevice, s));
+            DFB_CUDA(cudaEventRecord(job_ring_ev_[jr], s));
+        }
+        batch.jobs = job_ring_d_[jr];
+        batch.host_jobs = host_jobs;
         launches += launch_tvl1_fused(batch, device_, s);
         if (prm_.time_kernels) {
             DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][1], s));
@@ -562,6 +588,10 @@ class Tvl1 final : public FlowAlgorithm {
     }
     uint64_t unfused_px_iters_ = 0;
     float *unfused_scratch_ = nullptr;
+    static constexpr int kJobRing = 8;
+    FusedJob *job_ring_h_[kJobRing] = {}, *job_ring_d_[kJobRing] = {};
+    cudaEvent_t job_ring_ev_[kJobRing] = {};
+    long job_ring_next_ = 0;
 
     static constexpr size_t kMaxPartials = 1 << 16;
 

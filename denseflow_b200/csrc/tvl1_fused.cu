@@ -28,6 +28,7 @@
 // (per-CTA partial -> every CTA sums all partials identically), so every CTA takes the same
 // branch of the A.4 state machine and results are run-to-run deterministic.
 #include <cfloat>
+#include <cstring>
 
 
 #include <mutex>
@@ -64,6 +65,7 @@ struct Smem {
     unsigned long long prof[32];
     int prog[kWarps];  // per-warp progress counters of the tile loop (see process_tile)
     unsigned long long tma_bar;  // mbarrier the TMA tile loads complete on
+    FusedJob job;                // this lane's job description (copied from the device-memory ring at kernel start)
 };
 
 __device__ __forceinline__ float4 ld_cg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
@@ -550,12 +552,23 @@ struct Prof {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const __grid_constant__ FusedBatch batch) {
+// where a CTA finds its lane's job: the parameter bank (<= 16 lanes), or a copy in shared memory of the device-memory ring entry
+__device__ __forceinline__ const FusedJob &job_of(const FusedBatchParams &batch, int lane_id, Smem &) { return batch.job[lane_id]; }
+__device__ __forceinline__ const FusedJob &job_of(const FusedBatch &batch, int lane_id, Smem &sm) {
+    const int *src = reinterpret_cast<const int *>(batch.jobs + lane_id);
+    int *dst = reinterpret_cast<int *>(&sm.job);
+    for (int i = threadIdx.x; i < (int)(sizeof(FusedJob) / sizeof(int)); i += kThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
+    return sm.job;
+}
+
+template <class Batch>
+__global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const __grid_constant__ Batch batch) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int G = batch.group;
     const int lane_id = blockIdx.x / G, bid = blockIdx.x - lane_id * G;
-    const FusedJob &job = batch.job[lane_id];
+    const FusedJob &job = job_of(batch, lane_id, sm);
     const Tvl1Consts c = job.c;  // by value: the job is indexed dynamically in the parameter bank
     unsigned epoch = 0;
     unsigned *bar = job.sync;
@@ -709,6 +722,17 @@ int fused_num_sms(int device) {
     return num_sms[device];
 }
 
+template <class Batch>
+static void configure_kernel() {
+    DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair<Batch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair<Batch>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int resident = 0;
+    DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_tvl1_pair<Batch>, kThreads, sizeof(Smem)));
+    if (resident < kFusedCtasPerSm)
+        throw std::runtime_error("k_tvl1_pair: only " + std::to_string(resident) + " CTA(s) fit an SM, the launch geometry needs " +
+                                 std::to_string(kFusedCtasPerSm));
+}
+
 int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
     // the opt-in shared-memory size is a per-device function attribute: handles on several devices may live in one process
     static std::mutex mtx;
@@ -717,13 +741,8 @@ int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
         std::lock_guard<std::mutex> lk(mtx);
         const int d = device >= 0 && device < 64 ? device : 0;
         if (!configured[d]) {
-            DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-            DFB_CUDA(cudaFuncSetAttribute(k_tvl1_pair, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            int resident = 0;
-            DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_tvl1_pair, kThreads, sizeof(Smem)));
-            if (resident < kFusedCtasPerSm)
-                throw std::runtime_error("k_tvl1_pair: only " + std::to_string(resident) + " CTA(s) fit an SM, the launch geometry needs " +
-                                         std::to_string(kFusedCtasPerSm));
+            configure_kernel<FusedBatch>();
+            configure_kernel<FusedBatchParams>();
             configured[d] = true;
         }
     }
@@ -736,13 +755,19 @@ int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
     cfg.dynamicSmemBytes = sizeof(Smem);
     cfg.stream = s;
     cudaLaunchAttribute attrs[1];
-    int na = 0;
-    attrs[na].id = cudaLaunchAttributeCooperative;
-    attrs[na].val.cooperative = 1;
-    ++na;
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = na;
-    DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair, batch));
+    cfg.numAttrs = 1;
+    if (batch.njobs <= kFusedParamLanes) {
+        FusedBatchParams pb;
+        pb.njobs = batch.njobs;
+        pb.group = batch.group;
+        std::memcpy(pb.job, batch.host_jobs, sizeof(FusedJob) * batch.njobs);
+        DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatchParams>, pb));
+    } else {
+        DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatch>, batch));
+    }
     return 1;
 }
 
