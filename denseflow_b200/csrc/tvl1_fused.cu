@@ -142,14 +142,16 @@ __device__ __forceinline__ void phase_warp(const int G, const int bid, const Fus
     const float *u1 = L.u1[cur], *u2 = L.u2[cur];
     const float *__restrict__ I1 = L.I1;
     const float *I1x = job.I1x, *I1y = job.I1y;  // written before the last grid barrier (which invalidated L1)
-    const int total = H * W;
+    // two pixels per thread and trip — the same column of two consecutive rows, so the two 6 x 6 tap windows share five rows in
+    // L1 (the phase is latency-bound at 16 warps / SM: 64 independent gathers in flight per thread)
+    const int hrows = (H + 1) >> 1;
+    const int total = hrows * W;
     const int stride = G * kThreads;
-    // two pixels per thread and trip: 96 independent gathers in flight (the phase is latency-bound at 16 warps / SM)
-    for (int i = bid * kThreads + threadIdx.x; i < total; i += 2 * stride) {
-        const int i2 = i + stride;
-        const bool has2 = i2 < total;
-        const int y = i / W, x = i - y * W;
-        const int y2 = has2 ? i2 / W : y, x2 = has2 ? i2 - y2 * W : x;
+    for (int i = bid * kThreads + threadIdx.x; i < total; i += stride) {
+        const int yy = i / W, x = i - yy * W;
+        const int y = 2 * yy;
+        const bool has2 = y + 1 < H;
+        const int y2 = has2 ? y + 1 : y, x2 = x;
         const size_t o = (size_t)y * P + x, o2 = (size_t)y2 * P + x2;
         float ix, iy, g, rc, jx, jy, g2, rc2;
         tvl1_warp_px_window(I1, I1x, I1y, W, H, P, x, y, u1[o], u2[o], __ldg(L.I0 + o), ix, iy, g, rc);

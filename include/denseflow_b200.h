@@ -58,13 +58,15 @@ const char *dfb_last_error(const dfb_handle *h);
 
 /*
  * Algorithm hyper-parameters.  The reference never sets any (always create() defaults); these exist
- * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations"
- * "scale_step"; engine knobs: "fused" (1 = persistent fused primal+dual kernel [default], 0 = one
- * kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile),
- * "lanes" (pairs solved side by side per launch, 0 = auto, up to 16); "scale_step" must not exceed the default 0.8 the workspace is sized for, "flag_sync" (1 = neighbour-warp progress flags
- * in the tile loop [default], 0 = CTA-wide barriers), "use_tma" (1 = TMA staging of the shared-memory tiles [default]),
- * "time_kernels" (CUDA-event timing of the fused kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma" (winSize 13, polyN 5, pyrScale 0.5 are fixed).
- * Every combination of the engine knobs produces bit-identical flows.
+ * for tests and benchmarks.  tvl1: "tau" "lambda" "theta" "nscales" "warps" "epsilon" "iterations" "scale_step" (must not
+ * exceed the default 0.8 the workspace is sized for); engine knobs: "fused" (1 = persistent fused primal+dual kernel
+ * [default], 0 = one kernel per half-step, the reference's launch structure), "fused_k" (iterations kept on chip per tile
+ * visit, default 8), "lanes" (pairs solved side by side per launch, 0 = auto [default], up to 64), "flag_sync" (1 =
+ * neighbour-warp progress flags in the tile loop [default], 0 = CTA-wide barriers), "use_tma" (1 = TMA staging of the
+ * shared-memory tiles [default]), "prefetch" (1 = L2 prefetch of a CTA's next tile during the iterations [default]),
+ * "time_kernels" (CUDA-event timing of the dominant kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma"
+ * (winSize 13, polyN 5, pyrScale 0.5 are fixed), "use_tma" (1 = persistent TMA-staged iteration kernel [default], 0 = the
+ * LDG-staged one), "time_kernels".  Every combination of the engine knobs produces bit-identical flows.
  */
 int dfb_set_param(dfb_handle *h, const char *name, double value);
 int dfb_get_param(const dfb_handle *h, const char *name, double *value);
