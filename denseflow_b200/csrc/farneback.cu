@@ -181,26 +181,36 @@ __global__ void __launch_bounds__(256) k_poly_exp(Plane src, Plane5 R, const Far
 __constant__ float c_border[6] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f, 1.f};
 
 // ---- B.4 updateMatrices ------------------------------------------------------------------------------
-// r0[5]: the five R0 planes at (x, y), loaded by the caller (the iteration kernel fetches them at the start of a tile,
-// long before the flow that the R1 gather depends on exists)
-__device__ __forceinline__ void update_matrices_px_r0(int x, int y, int w, int h, int pitch, float dx, float dy, const float r0[5],
-                                                      const Plane5 &R1, float m[5]) {
+// ---- B.4 in three steps, so that two horizontally adjacent pixels can share their R1 taps -----------------------------------
+struct UmCoord {
+    int x1, y1;
+    float fx, fy;
+    bool inside;
+};
+__device__ __forceinline__ UmCoord um_coord(int x, int y, float dx, float dy, int w, int h) {
+    UmCoord c;
     float fx = x + dx, fy = y + dy;
-    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= x1;
-    fy -= y1;
+    c.x1 = (int)floorf(fx);
+    c.y1 = (int)floorf(fy);
+    c.fx = fx - c.x1;
+    c.fy = fy - c.y1;
+    c.inside = c.x1 >= 0 && c.y1 >= 0 && c.x1 < w - 1 && c.y1 < h - 1;
+    return c;
+}
+// one bilinear sample, always written in this form (the compiler's multiply-add contraction is part of the result)
+__device__ __forceinline__ float um_bilinear(float a00, float a01, float a10, float a11, float v00, float v01, float v10, float v11) {
+    return a00 * v00 + a01 * v01 + a10 * v10 + a11 * v11;
+}
+// r0[5]: the five R0 planes at (x, y); s[5]: the five bilinear samples of R1 (ignored when the tap cell is outside the image)
+__device__ __forceinline__ void um_finish(int x, int y, int w, int h, float dx, float dy, const float r0[5], bool inside, const float s[5],
+                                          float m[5]) {
     float r2, r3, r4, r5, r6;
-    if (x1 >= 0 && y1 >= 0 && x1 < w - 1 && y1 < h - 1) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t j = (size_t)y1 * pitch + x1;
-        r2 = a00 * R1.p[0][j] + a01 * R1.p[0][j + 1] + a10 * R1.p[0][j + pitch] + a11 * R1.p[0][j + pitch + 1];
-        r3 = a00 * R1.p[1][j] + a01 * R1.p[1][j + 1] + a10 * R1.p[1][j + pitch] + a11 * R1.p[1][j + pitch + 1];
-        r4 = a00 * R1.p[2][j] + a01 * R1.p[2][j + 1] + a10 * R1.p[2][j + pitch] + a11 * R1.p[2][j + pitch + 1];
-        r5 = a00 * R1.p[3][j] + a01 * R1.p[3][j + 1] + a10 * R1.p[3][j + pitch] + a11 * R1.p[3][j + pitch + 1];
-        r6 = a00 * R1.p[4][j] + a01 * R1.p[4][j + 1] + a10 * R1.p[4][j + pitch] + a11 * R1.p[4][j + pitch + 1];
-        r4 = (r0[2] + r4) * 0.5f;
-        r5 = (r0[3] + r5) * 0.5f;
-        r6 = (r0[4] + r6) * 0.25f;
+    if (inside) {
+        r2 = s[0];
+        r3 = s[1];
+        r4 = (r0[2] + s[2]) * 0.5f;
+        r5 = (r0[3] + s[3]) * 0.5f;
+        r6 = (r0[4] + s[4]) * 0.25f;
     } else {
         r2 = r3 = 0.f;
         r4 = r0[2];
@@ -222,6 +232,45 @@ __device__ __forceinline__ void update_matrices_px_r0(int x, int y, int w, int h
     m[2] = r5 * r5 + r6 * r6;
     m[3] = r4 * r2 + r6 * r3;
     m[4] = r6 * r2 + r5 * r3;
+}
+__device__ __forceinline__ void um_sample(const UmCoord &c, int pitch, const Plane5 &R1, float s[5]) {
+    const float a00 = (1.f - c.fx) * (1.f - c.fy), a01 = c.fx * (1.f - c.fy), a10 = (1.f - c.fx) * c.fy, a11 = c.fx * c.fy;
+    const size_t j = (size_t)c.y1 * pitch + c.x1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s[k] = um_bilinear(a00, a01, a10, a11, R1.p[k][j], R1.p[k][j + 1], R1.p[k][j + pitch], R1.p[k][j + pitch + 1]);
+}
+// r0[5] loaded by the caller (the iteration kernel fetches them at the start of a tile, long before the flow that the R1 gather
+// depends on exists)
+__device__ __forceinline__ void update_matrices_px_r0(int x, int y, int w, int h, int pitch, float dx, float dy, const float r0[5],
+                                                      const Plane5 &R1, float m[5]) {
+    const UmCoord c = um_coord(x, y, dx, dy, w, h);
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c.inside) um_sample(c, pitch, R1, s);
+    um_finish(x, y, w, h, dx, dy, r0, c.inside, s, m);
+}
+// Two horizontally adjacent pixels (x, y), (x + 1, y): with a smooth flow their tap cells are neighbours (same row, x1 one apart)
+// and share a column, so the pair needs 6 gathers per plane instead of 8.  Same samples, same arithmetic.
+__device__ __forceinline__ void update_matrices_2px_r0(int xa, int xb, int y, int w, int h, int pitch, const float dx[2], const float dy[2],
+                                                       const float r0[2][5], const Plane5 &R1, float m[2][5]) {
+    const UmCoord ca = um_coord(xa, y, dx[0], dy[0], w, h), cb = um_coord(xb, y, dx[1], dy[1], w, h);
+    float sa[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ca.inside && cb.inside && ca.y1 == cb.y1 && cb.x1 == ca.x1 + 1) {
+        const float a00 = (1.f - ca.fx) * (1.f - ca.fy), a01 = ca.fx * (1.f - ca.fy), a10 = (1.f - ca.fx) * ca.fy, a11 = ca.fx * ca.fy;
+        const float b00 = (1.f - cb.fx) * (1.f - cb.fy), b01 = cb.fx * (1.f - cb.fy), b10 = (1.f - cb.fx) * cb.fy, b11 = cb.fx * cb.fy;
+        const size_t j = (size_t)ca.y1 * pitch + ca.x1;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float t0 = R1.p[k][j], t1 = R1.p[k][j + 1], t2 = R1.p[k][j + 2];
+            const float u0 = R1.p[k][j + pitch], u1 = R1.p[k][j + pitch + 1], u2 = R1.p[k][j + pitch + 2];
+            sa[k] = um_bilinear(a00, a01, a10, a11, t0, t1, u0, u1);
+            sb[k] = um_bilinear(b00, b01, b10, b11, t1, t2, u1, u2);
+        }
+    } else {
+        if (ca.inside) um_sample(ca, pitch, R1, sa);
+        if (cb.inside) um_sample(cb, pitch, R1, sb);
+    }
+    um_finish(xa, y, w, h, dx[0], dy[0], r0[0], ca.inside, sa, m[0]);
+    um_finish(xb, y, w, h, dx[1], dy[1], r0[1], cb.inside, sb, m[1]);
 }
 
 __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, float dx, float dy, const Plane5 &R0,
@@ -381,8 +430,12 @@ __device__ __forceinline__ void box_tile_compute(const float *raw /* [5][kBoxPla
             nfy[o] = (b[o][2] * b[o][3] - b[o][1] * b[o][4]) * det_inv;
         }
         if (rebuild) {
+            if (PX == 2) {
+                update_matrices_2px_r0(min(x0 + tx0, w - 1), min(x0 + tx0 + 1, w - 1), yc, w, h, pitch, nfx, nfy, r0pre, R1, m);
+            } else {
 #pragma unroll
-            for (int o = 0; o < PX; ++o) update_matrices_px_r0(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], r0pre[o], R1, m[o]);
+                for (int o = 0; o < PX; ++o) update_matrices_px_r0(min(x0 + tx0 + o, w - 1), yc, w, h, pitch, nfx[o], nfy[o], r0pre[o], R1, m[o]);
+            }
         }
 #pragma unroll
         for (int o = 0; o < PX; ++o) {
