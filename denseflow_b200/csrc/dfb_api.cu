@@ -191,22 +191,32 @@ int batch_host(dfb_handle *h, const uint8_t *const *frames, int n_frames, int st
 
     int uploaded = 0;  // frames [0, uploaded) have H2D + pyramid enqueued
     auto upload_until = [&](int last) {
-        for (; uploaded <= last; ++uploaded) {
-            const int f = uploaded, r = f % FR;
-            if (f >= FR) DFB_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_pyr[r], 0));  // ring slot's pyramid is built
-            const uint8_t *src = frames[f];
-            if (!is_pinned_host(src)) {
-                // the pinned staging buffer of this ring slot is free once its previous H2D finished
-                if (f >= FR) DFB_CUDA(cudaEventSynchronize(h->ev_in[r]));
-                std::memcpy(stage_frame(h, r), src, fbytes);
-                src = h->h_frame[r];
+        // sub-batches of at most FR frames: one H2D per frame on s_in, then ONE batched preparation on s_compute (the per-frame
+        // stages are launch-latency-bound; a device ring slot is reused only after its frame has been prepared)
+        while (uploaded <= last) {
+            const int first = uploaded, cnt = std::min(last - uploaded + 1, FR);
+            const uint8_t *srcs[FR];
+            int slots[FR];
+            for (int i = 0; i < cnt; ++i) {
+                const int f = first + i, r = f % FR;
+                if (f >= FR) DFB_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_pyr[r], 0));  // ring slot's pyramid is built
+                const uint8_t *src = frames[f];
+                if (!is_pinned_host(src)) {
+                    // the pinned staging buffer of this ring slot is free once its previous H2D finished
+                    if (f >= FR) DFB_CUDA(cudaEventSynchronize(h->ev_in[r]));
+                    std::memcpy(stage_frame(h, r), src, fbytes);
+                    src = h->h_frame[r];
+                }
+                DFB_CUDA(cudaMemcpy2DAsync(h->d_frame[r], h->d_frame_pitch, src, w, w, hh, cudaMemcpyHostToDevice, h->s_in));
+                DFB_CUDA(cudaEventRecord(h->ev_in[r], h->s_in));
+                h->counters.h2d_bytes += fbytes;
+                srcs[i] = h->d_frame[r];
+                slots[i] = f % nslots;
             }
-            DFB_CUDA(cudaMemcpy2DAsync(h->d_frame[r], h->d_frame_pitch, src, w, w, hh, cudaMemcpyHostToDevice, h->s_in));
-            DFB_CUDA(cudaEventRecord(h->ev_in[r], h->s_in));
-            h->counters.h2d_bytes += fbytes;
-            DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_in[r], 0));
-            alg.prepare_frame(h->d_frame[r], h->d_frame_pitch, w, hh, f % nslots, h->s_compute);
-            DFB_CUDA(cudaEventRecord(h->ev_pyr[r], h->s_compute));
+            DFB_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_in[(first + cnt - 1) % FR], 0));  // s_in is in order: the last covers all
+            alg.prepare_frames(cnt, srcs, h->d_frame_pitch, w, hh, slots, h->s_compute);
+            for (int i = 0; i < cnt; ++i) DFB_CUDA(cudaEventRecord(h->ev_pyr[(first + i) % FR], h->s_compute));
+            uploaded += cnt;
         }
     };
 
@@ -461,8 +471,15 @@ int dfb_calc_batch_device(dfb_handle *h, const uint8_t *frames, int n_frames, in
         std::vector<FlowAlgorithm::PairJob> jobs(B);
         for (int j0 = 0; j0 < M; j0 += B) {
             const int m = std::min(B, M - j0);
-            for (; prepared <= j0 + m - 1 + astep; ++prepared)
-                alg.prepare_frame(frames + (size_t)prepared * fbytes, width, width, height, prepared % nslots, s);
+            {
+                std::vector<const uint8_t *> srcs;
+                std::vector<int> slots;
+                for (; prepared <= j0 + m - 1 + astep; ++prepared) {
+                    srcs.push_back(frames + (size_t)prepared * fbytes);
+                    slots.push_back(prepared % nslots);
+                }
+                if (!srcs.empty()) alg.prepare_frames((int)srcs.size(), srcs.data(), width, width, height, slots.data(), s);
+            }
             for (int i = 0; i < m; ++i) {
                 const int j = j0 + i;
                 const int a = step > 0 ? j : j + astep;
@@ -715,8 +732,15 @@ int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_f
             upload_until(last_frame + 1);
             DFB_CUDA(cudaStreamWaitEvent(h->s_compute, ev_frame[last_frame], 0));
             if (g >= 2) DFB_CUDA(cudaStreamWaitEvent(h->s_compute, ev_enc[slot], 0));  // the planes of group g-2 have been encoded
-            for (; prepared <= last_frame; ++prepared)
-                alg.prepare_frame(h->pb_frames + fpx * prepared, dw, dw, dh, prepared % nslots, h->s_compute);
+            {
+                std::vector<const uint8_t *> srcs;
+                std::vector<int> slots;
+                for (; prepared <= last_frame; ++prepared) {
+                    srcs.push_back(h->pb_frames + fpx * prepared);
+                    slots.push_back(prepared % nslots);
+                }
+                if (!srcs.empty()) alg.prepare_frames((int)srcs.size(), srcs.data(), dw, dw, dh, slots.data(), h->s_compute);
+            }
             for (int i = 0; i < m; ++i) {
                 const int j = j0 + i;
                 FlowAlgorithm::PairJob &pj = jobs[i];

@@ -29,6 +29,10 @@ class FlowAlgorithm {
     virtual void ensure_slots(int n) = 0;
     // per-frame work: u8 -> fp32 (+ pyramid)
     virtual void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) = 0;
+    // several frames of one size at once (engines whose per-frame stages are launch-latency-bound batch them)
+    virtual void prepare_frames(int n, const uint8_t *const *srcs, size_t pitch_bytes, int w, int h, const int *slots, cudaStream_t s) {
+        for (int i = 0; i < n; ++i) prepare_frame(srcs[i], pitch_bytes, w, h, slots[i], s);
+    }
     // per-pair work: flow(slot_a -> slot_b) into interleaved float2 rows
     virtual void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes,
                        cudaStream_t s) = 0;

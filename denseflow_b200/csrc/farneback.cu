@@ -52,7 +52,30 @@ struct GaussKernel {
 
 constexpr int GT = 32;  // tile edge
 
-__global__ void __launch_bounds__(256) k_gauss_blur(Plane src, Plane dst, const GaussKernel gk) {
+// Frame preparation is batched like the pairs: every stage is launched once for all the new frames of a batch (blockIdx.z =
+// frame).  At these sizes each stage is launch-latency-bound (~18 small launches per frame), so a 17-frame batch went from ~300
+// launches to 18.
+constexpr int kMaxPrep = 16;
+struct PrepBatch {
+    const uint8_t *src[kMaxPrep];
+    float *frame[kMaxPrep], *vn[kMaxPrep], *img[kMaxPrep];
+    float *r[kMaxPrep];  // first R plane of the current level in the frame's slot
+};
+
+__global__ void k_farn_u8_to_f32(const __grid_constant__ PrepBatch pb, size_t src_pitch, int w, int h, int pitch) {
+    const int x0 = 4 * (blockIdx.x * 32 + threadIdx.x), y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= h || x0 >= w) return;
+    const uint8_t *row = pb.src[blockIdx.z] + (size_t)y * src_pitch;
+    float4 v;
+    v.x = row[x0];
+    v.y = x0 + 1 < w ? row[x0 + 1] : 0.f;
+    v.z = x0 + 2 < w ? row[x0 + 2] : 0.f;
+    v.w = x0 + 3 < w ? row[x0 + 3] : 0.f;
+    *reinterpret_cast<float4 *>(pb.frame[blockIdx.z] + (size_t)y * pitch + x0) = v;  // pitch % 32 == 0: in-bounds
+}
+
+__global__ void __launch_bounds__(256) k_gauss_blur(const __grid_constant__ PrepBatch pb, int fw, int fh, int fpitch, const GaussKernel gk) {
+    const Plane src{pb.frame[blockIdx.z], fw, fh, fpitch}, dst{pb.img[blockIdx.z], fw, fh, fpitch};
     extern __shared__ float smem[];  // [GT][GT + 2*half]
     const int half = gk.half;
     const int sw = GT + 2 * half;
@@ -85,7 +108,9 @@ __global__ void __launch_bounds__(256) k_gauss_blur(Plane src, Plane dst, const 
 // pass only on the 2 * H_level rows the resize touches, the horizontal pass only at the 2 x 2 taps of each level pixel —
 // with the same operation order per value (vertical first; centre tap, then symmetric pairs), so the level image is
 // bit-identical to blur-then-resize while the work drops from ~70 to ~24 taps per full-resolution pixel and level set.
-__global__ void __launch_bounds__(256) k_gauss_vert_rows(Plane src, Plane vn /* 2*Hl rows */, float rfy, const GaussKernel gk) {
+__global__ void __launch_bounds__(256) k_gauss_vert_rows(const __grid_constant__ PrepBatch pb, int fw, int fh, int fpitch, int lh, float rfy,
+                                                         const GaussKernel gk) {
+    const Plane src{pb.frame[blockIdx.z], fw, fh, fpitch}, vn{pb.vn[blockIdx.z], fw, 2 * lh, fpitch};  // vn: 2 * H_level rows
     const int x = blockIdx.x * 256 + threadIdx.x;
     const int ri = blockIdx.y;  // row pair index: level row ri >> 1, tap ri & 1
     if (x >= src.w) return;
@@ -98,7 +123,9 @@ __global__ void __launch_bounds__(256) k_gauss_vert_rows(Plane src, Plane vn /* 
     vn.p[(size_t)ri * vn.pitch + x] = acc;
 }
 
-__global__ void __launch_bounds__(256) k_gauss_horz_resize(Plane vn, int src_w, int src_h, Plane dst, float rfx, float rfy, const GaussKernel gk) {
+__global__ void __launch_bounds__(256) k_gauss_horz_resize(const __grid_constant__ PrepBatch pb, int src_w, int src_h, int fpitch, int lw, int lh,
+                                                           int lpitch, float rfx, float rfy, const GaussKernel gk) {
+    const Plane vn{pb.vn[blockIdx.z], src_w, 2 * lh, fpitch}, dst{pb.img[blockIdx.z], lw, lh, lpitch};
     const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
     if (dx >= dst.w || dy >= dst.h) return;
     const float sx = dx * rfx, sy = dy * rfy;
@@ -129,7 +156,10 @@ __global__ void __launch_bounds__(256) k_gauss_horz_resize(Plane vn, int src_w, 
 constexpr int PT = 32;
 
 template <int N>
-__global__ void __launch_bounds__(256) k_poly_exp(Plane src, Plane5 R, const FarnConsts c) {
+__global__ void __launch_bounds__(256) k_poly_exp(const __grid_constant__ PrepBatch pb, int lw, int lh, int lpitch, size_t plane_elems, const FarnConsts c) {
+    const Plane src{pb.img[blockIdx.z], lw, lh, lpitch};
+    float *const rb = pb.r[blockIdx.z];
+    const Plane5 R{{rb, rb + plane_elems, rb + 2 * plane_elems, rb + 3 * plane_elems, rb + 4 * plane_elems}, lw, lh, lpitch};
     __shared__ float t0[PT][PT + 2 * N], t1[PT][PT + 2 * N], t2[PT][PT + 2 * N];
     constexpr int sw = PT + 2 * N;
     const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT;
@@ -818,6 +848,9 @@ class Farneback final : public FlowAlgorithm {
         for (auto p : extra_slots_) cudaFree(p);
         for (auto &l : lanes_) cudaFree(l.own);
         if (d_maps_) cudaFree(d_maps_);
+        for (auto &p : prep_)
+            if (p.own)
+                for (float *q : {p.frame, p.blurred, p.img}) cudaFree(q);
         for (auto &e : timing_ev_)
             for (auto ev : e)
                 if (ev) cudaEventDestroy(ev);
@@ -886,34 +919,50 @@ class Farneback final : public FlowAlgorithm {
     // per-frame work (B.2, B.3): u8 -> fp32, then for every level: Gaussian blur of the FULL-resolution frame,
     // bilinear resize to the level, polynomial expansion into the slot's R planes
     void prepare_frame(const uint8_t *src, size_t pitch_bytes, int w, int h, int slot, cudaStream_t s) override {
+        prepare_frames(1, &src, pitch_bytes, w, h, &slot, s);
+    }
+    void prepare_frames(int n, const uint8_t *const *srcs, size_t pitch_bytes, int w, int h, const int *slots, cudaStream_t s) override {
         const LevelSet ls = levels_for(w, h, false);
         const int pitch_full = round_up(w, 32);
-        const Plane frame{frame_, w, h, pitch_full};
-        launch_u8_to_f32(src, pitch_bytes, frame, s);
-        ++launches;
         const FarnConsts pc = poly_constants(prm_.poly_n, prm_.poly_sigma);
-        for (int l = 0; l < ls.n; ++l) {
-            const Level &L = ls.lv[l];
-            const GaussKernel gk = gaussian_kernel(L.smooth, L.sigma);
-            if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
-            const Plane img{img_, L.w, L.h, L.pitch};
-            const float rfx = (float)(1.0 / ((double)L.w / (double)w)), rfy = (float)(1.0 / ((double)L.h / (double)h));
-            if (L.w == w && L.h == h) {
-                // full resolution: the resize is the identity (weights 1, 0, 0, 0), blur straight into the level image
-                k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT)), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(frame, img, gk);
+        for (int f0 = 0; f0 < n; f0 += kMaxPrep) {
+            const int nf = std::min(kMaxPrep, n - f0);
+            ensure_prep_scratch(nf);
+            PrepBatch pb{};
+            for (int i = 0; i < nf; ++i) {
+                pb.src[i] = srcs[f0 + i];
+                pb.frame[i] = prep_[i].frame;
+                pb.vn[i] = prep_[i].blurred;
+                pb.img[i] = prep_[i].img;
+            }
+            k_farn_u8_to_f32<<<dim3(ceil_div(w, 128), ceil_div(h, 8), nf), dim3(32, 8), 0, s>>>(pb, pitch_bytes, w, h, pitch_full);
+            DFB_KERNEL_CHECK();
+            ++launches;
+            for (int l = 0; l < ls.n; ++l) {
+                const Level &L = ls.lv[l];
+                const GaussKernel gk = gaussian_kernel(L.smooth, L.sigma);
+                if (gk.half > kMaxHalf) throw std::runtime_error("farn: smoothing kernel too large");
+                const float rfx = (float)(1.0 / ((double)L.w / (double)w)), rfy = (float)(1.0 / ((double)L.h / (double)h));
+                const size_t pe = ((size_t)L.pitch * (L.h + 1) + 63) & ~size_t(63);
+                for (int i = 0; i < nf; ++i) pb.r[i] = slots_.at(slots[f0 + i]) + L.r_off;
+                if (L.w == w && L.h == h) {
+                    // full resolution: the resize is the identity (weights 1, 0, 0, 0), blur straight into the level image
+                    k_gauss_blur<<<dim3(ceil_div(w, GT), ceil_div(h, GT), nf), 256, GT * (GT + 2 * gk.half) * sizeof(float), s>>>(pb, w, h, pitch_full, gk);
+                    DFB_KERNEL_CHECK();
+                    launches += 1;
+                } else {
+                    // vn: 2 * H_level <= h rows, fits the full-resolution scratch plane
+                    k_gauss_vert_rows<<<dim3(ceil_div(w, 256), 2 * L.h, nf), 256, 0, s>>>(pb, w, h, pitch_full, L.h, rfy, gk);
+                    DFB_KERNEL_CHECK();
+                    k_gauss_horz_resize<<<dim3(ceil_div(L.w, 32), ceil_div(L.h, 8), nf), dim3(32, 8), 0, s>>>(pb, w, h, pitch_full, L.w, L.h, L.pitch, rfx,
+                                                                                                             rfy, gk);
+                    DFB_KERNEL_CHECK();
+                    launches += 2;
+                }
+                k_poly_exp<5><<<dim3(ceil_div(L.w, PT), ceil_div(L.h, PT), nf), 256, 0, s>>>(pb, L.w, L.h, L.pitch, pe, pc);
                 DFB_KERNEL_CHECK();
                 launches += 1;
-            } else {
-                const Plane vn{blurred_, w, 2 * L.h, pitch_full};  // 2 * H_level <= h rows: fits the full-resolution scratch plane
-                k_gauss_vert_rows<<<dim3(ceil_div(w, 256), 2 * L.h), 256, 0, s>>>(frame, vn, rfy, gk);
-                DFB_KERNEL_CHECK();
-                k_gauss_horz_resize<<<dim3(ceil_div(L.w, 32), ceil_div(L.h, 8)), dim3(32, 8), 0, s>>>(vn, w, h, img, rfx, rfy, gk);
-                DFB_KERNEL_CHECK();
-                launches += 2;
             }
-            k_poly_exp<5><<<dim3(ceil_div(L.w, PT), ceil_div(L.h, PT)), 256, 0, s>>>(img, r_planes(slot, L), pc);
-            DFB_KERNEL_CHECK();
-            launches += 1;
         }
     }
 
@@ -1061,7 +1110,25 @@ class Farneback final : public FlowAlgorithm {
     FarnParams prm_;
     Slab slab_;
     std::vector<float *> slots_, extra_slots_;
-    float *frame_ = nullptr, *blurred_ = nullptr, *img_ = nullptr;
+    float *frame_ = nullptr, *blurred_ = nullptr, *img_ = nullptr;  // scratch of the first frame of a preparation batch (slab)
+    struct PrepScratch {
+        float *frame = nullptr, *blurred = nullptr, *img = nullptr;
+        bool own = false;
+    };
+    std::vector<PrepScratch> prep_;
+    void ensure_prep_scratch(int n) {
+        if (prep_.empty()) prep_.push_back(PrepScratch{frame_, blurred_, img_, false});
+        while ((int)prep_.size() < n) {
+            PrepScratch p;
+            p.own = true;
+            for (float **q : {&p.frame, &p.blurred, &p.img}) {
+                DFB_CUDA(cudaMalloc(q, plane_elems_ * sizeof(float)));
+                DFB_CUDA(cudaMemset(*q, 0, plane_elems_ * sizeof(float)));
+            }
+            DFB_CUDA(cudaDeviceSynchronize());
+            prep_.push_back(p);
+        }
+    }
     // per-pair workspace: M (two buffers of five planes) and the flow of the current + previous level
     struct Lane {
         float *own = nullptr;

@@ -40,6 +40,17 @@ struct Tvl1Consts {
 // ---- stand-alone kernels (one launch per half-step: the reference's launch structure) -------
 void launch_u8_to_f32(const uint8_t *src, size_t src_pitch_bytes, Plane dst, cudaStream_t s);
 void launch_resize_linear(Plane src, Plane dst, float fx, float fy, float post_mul, cudaStream_t s);
+// the two per-frame stages for several frames of one size at once (blockIdx.z = frame): each launch is latency-bound, a
+// 64-frame clip needs 5 launches instead of 320
+constexpr int kMaxFrameBatch = 16;
+struct FramePtrs {
+    const uint8_t *src[kMaxFrameBatch];
+    float *base[kMaxFrameBatch];  // the frame's pyramid slot
+};
+void launch_u8_to_f32_batch(const FramePtrs &fp, int n, size_t src_pitch_bytes, int w, int h, int pitch, cudaStream_t s);
+// level (src_off, sw, sh, sp) -> level (dst_off, dw, dh, dp) of every frame's slot
+void launch_resize_linear_batch(const FramePtrs &fp, int n, size_t src_off, int sw, int sh, int sp, size_t dst_off, int dw, int dh, int dp, float fx,
+                                float fy, cudaStream_t s);
 void launch_centered_gradient(Plane src, Plane dx, Plane dy, cudaStream_t s);
 void launch_warp_backward(Plane I0, Plane I1, Plane I1x, Plane I1y, Plane u1, Plane u2, Plane I1wx, Plane I1wy,
                           Plane grad, Plane rho_c, cudaStream_t s);

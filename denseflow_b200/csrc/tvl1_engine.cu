@@ -151,6 +151,29 @@ class Tvl1 final : public FlowAlgorithm {
         }
     }
 
+    void prepare_frames(int n, const uint8_t *const *srcs, size_t pitch_bytes, int w, int h, const int *slots, cudaStream_t s) override {
+        LevelGeom lv[kMaxScales];
+        const int nl = level_geometry(w, h, lv);
+        const float finv = (float)(1.0 / prm_.scale_step);
+        for (int f0 = 0; f0 < n; f0 += kMaxFrameBatch) {
+            const int nf = std::min(kMaxFrameBatch, n - f0);
+            FramePtrs fp{};
+            for (int i = 0; i < nf; ++i) {
+                fp.src[i] = srcs[f0 + i];
+                fp.base[i] = slots_.at(slots[f0 + i]);
+            }
+            launch_u8_to_f32_batch(fp, nf, pitch_bytes, w, h, lv[0].pitch, s);
+            ++launches;
+            size_t off = 0;
+            for (int l = 1; l < nl; ++l) {
+                const size_t next = off + level_stride(l - 1);
+                launch_resize_linear_batch(fp, nf, off, lv[l - 1].w, lv[l - 1].h, lv[l - 1].pitch, next, lv[l].w, lv[l].h, lv[l].pitch, finv, finv, s);
+                ++launches;
+                off = next;
+            }
+        }
+    }
+
     void solve(int slot_a, int slot_b, int w, int h, float *flow_xy, size_t flow_pitch_bytes,
                cudaStream_t s) override {
         LevelGeom lv[kMaxScales];

@@ -54,6 +54,46 @@ __global__ void k_resize_linear(Plane src, Plane dst, float fx, float fy, float 
     dst.p[(size_t)dy * dst.pitch + dx] = out * post_mul;
 }
 
+__global__ void k_u8_to_f32_batch(const __grid_constant__ FramePtrs fp, size_t src_pitch, int w, int h, int pitch) {
+    const int x0 = 4 * (blockIdx.x * BX + threadIdx.x);
+    const int y = blockIdx.y * BY + threadIdx.y;
+    if (y >= h || x0 >= w) return;
+    const uint8_t *row = fp.src[blockIdx.z] + (size_t)y * src_pitch;
+    float4 v;
+    if (x0 + 3 < w && ((reinterpret_cast<uintptr_t>(row + x0) & 3) == 0)) {
+        const uchar4 q = *reinterpret_cast<const uchar4 *>(row + x0);
+        v = make_float4(q.x, q.y, q.z, q.w);
+    } else {
+        v.x = row[x0];
+        v.y = x0 + 1 < w ? row[x0 + 1] : 0.f;
+        v.z = x0 + 2 < w ? row[x0 + 2] : 0.f;
+        v.w = x0 + 3 < w ? row[x0 + 3] : 0.f;
+    }
+    *reinterpret_cast<float4 *>(fp.base[blockIdx.z] + (size_t)y * pitch + x0) = v;
+}
+
+// same arithmetic as k_resize_linear (post_mul = 1)
+__global__ void k_resize_linear_batch(const __grid_constant__ FramePtrs fp, size_t src_off, int sw, int sh, int sp, size_t dst_off, int dw, int dh,
+                                      int dp, float fx, float fy) {
+    const int dx = blockIdx.x * BX + threadIdx.x;
+    const int dy = blockIdx.y * BY + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    const float *src = fp.base[blockIdx.z] + src_off;
+    const float sx = dx * fx, sy = dy * fy;
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int x1r = min(x1, sw - 1), y1r = min(y1, sh - 1);
+    const int x2r = min(x2, sw - 1), y2r = min(y2, sh - 1);
+    const float *r1 = src + (size_t)y1r * sp;
+    const float *r2 = src + (size_t)y2r * sp;
+    float out = 0.f;
+    out = out + r1[x1r] * ((x2 - sx) * (y2 - sy));
+    out = out + r1[x2r] * ((sx - x1) * (y2 - sy));
+    out = out + r2[x1r] * ((x2 - sx) * (sy - y1));
+    out = out + r2[x2r] * ((sx - x1) * (sy - y1));
+    fp.base[blockIdx.z][dst_off + (size_t)dy * dp + dx] = out * 1.0f;
+}
+
 // A.2 step 1: half central differences, index-clamped.
 __global__ void k_centered_gradient(Plane src, Plane gx, Plane gy) {
     const int x = blockIdx.x * BX + threadIdx.x;
@@ -212,6 +252,17 @@ __global__ void k_quantise(const float *flow, size_t flow_pitch_bytes, int w, in
 
 void launch_u8_to_f32(const uint8_t *src, size_t src_pitch_bytes, Plane dst, cudaStream_t s) {
     k_u8_to_f32<<<grid2d(dst.w, dst.h, 4), dim3(BX, BY), 0, s>>>(src, src_pitch_bytes, dst);
+    DFB_KERNEL_CHECK();
+}
+void launch_u8_to_f32_batch(const FramePtrs &fp, int n, size_t src_pitch_bytes, int w, int h, int pitch, cudaStream_t s) {
+    const dim3 g = grid2d(w, h, 4);
+    k_u8_to_f32_batch<<<dim3(g.x, g.y, n), dim3(BX, BY), 0, s>>>(fp, src_pitch_bytes, w, h, pitch);
+    DFB_KERNEL_CHECK();
+}
+void launch_resize_linear_batch(const FramePtrs &fp, int n, size_t src_off, int sw, int sh, int sp, size_t dst_off, int dw, int dh, int dp, float fx,
+                                float fy, cudaStream_t s) {
+    const dim3 g = grid2d(dw, dh);
+    k_resize_linear_batch<<<dim3(g.x, g.y, n), dim3(BX, BY), 0, s>>>(fp, src_off, sw, sh, sp, dst_off, dw, dh, dp, fx, fy);
     DFB_KERNEL_CHECK();
 }
 void launch_resize_linear(Plane src, Plane dst, float fx, float fy, float post_mul, cudaStream_t s) {
