@@ -81,7 +81,9 @@ template <typename F> int guarded(dfb_handle *h, F &&f) {
         return f();
     } catch (const CudaError &e) {
         quiesce(h);
-        return fail(h, DFB_ERR_CUDA, e.what());
+        std::string info;
+        if (h && h->alg) info = h->alg->fault_info();
+        return fail(h, DFB_ERR_CUDA, info.empty() ? std::string(e.what()) : std::string(e.what()) + " [" + info + "]");
     } catch (const std::exception &e) {
         quiesce(h);
         return fail(h, DFB_ERR_INVALID_ARG, e.what());

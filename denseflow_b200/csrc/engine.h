@@ -49,6 +49,8 @@ class FlowAlgorithm {
         size_t q_pitch = 0;
     };
     virtual int max_concurrent_pairs(int w, int h) { (void)w; (void)h; return 1; }
+    // after a CUDA error: what the engine's own watchdogs recorded (empty if nothing)
+    virtual std::string fault_info() { return {}; }
     virtual void solve_batch(const PairJob *jobs, int n, int w, int h, cudaStream_t s) {
         for (int i = 0; i < n; ++i) solve(jobs[i].slot_a, jobs[i].slot_b, w, h, jobs[i].flow_xy, jobs[i].flow_pitch_bytes, s);
     }

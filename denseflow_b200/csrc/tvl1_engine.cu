@@ -11,6 +11,7 @@
 //                        state machine on the host (one stream sync per convergence check).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -37,12 +38,15 @@ struct Tvl1Params {
     int use_tma = 1;
     int prefetch = 1;
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
+    int serial_launches = 1;  // fused launches of all handles on one device execute one after another (event chain)
 };
 
 class Tvl1 final : public FlowAlgorithm {
   public:
     Tvl1(int device, int max_w, int max_h) : device_(device), max_w_(max_w), max_h_(max_h) {
         DFB_CUDA(cudaSetDevice(device_));
+        if (const char *e = std::getenv("DFB_TVL1_LANES")) prm_.lanes = std::max(0, std::min(atoi(e), kFusedMaxLanes));  // debugging aid
+        if (const char *e = std::getenv("DFB_TVL1_SERIAL_LAUNCHES")) prm_.serial_launches = atoi(e) != 0;         // debugging aid
         allocate();
     }
     ~Tvl1() override {
@@ -100,6 +104,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "time_kernels") prm_.time_kernels = v != 0;
         else if (k == "use_tma") prm_.use_tma = v != 0;
         else if (k == "prefetch") prm_.prefetch = v != 0;
+        else if (k == "serial_launches") prm_.serial_launches = v != 0;
         else if (k == "lanes") { if (v < 0 || v > kFusedMaxLanes) return false; prm_.lanes = (int)v; }
         else return false;
         return true;
@@ -119,6 +124,7 @@ class Tvl1 final : public FlowAlgorithm {
         else if (k == "time_kernels") *v = prm_.time_kernels;
         else if (k == "use_tma") *v = prm_.use_tma;
         else if (k == "prefetch") *v = prm_.prefetch;
+        else if (k == "serial_launches") *v = prm_.serial_launches;
         else if (k == "lanes") *v = prm_.lanes;
         else return false;
         return true;
@@ -286,6 +292,15 @@ class Tvl1 final : public FlowAlgorithm {
     }
 
     void begin_batch() override { pair_log_count_ = 0; }
+    std::string fault_info() override {
+        for (size_t i = 0; i < lanes_.size(); ++i) {
+            const volatile unsigned *st = lanes_[i].host_ctl->stall;
+            if (st[0])
+                return "k_tvl1_pair grid-barrier watchdog: CTA " + std::to_string(st[1]) + " (lane " + std::to_string(st[5]) + ", " +
+                       std::to_string(st[4]) + " CTAs per lane) waited for arrival count " + std::to_string(st[2]) + ", saw " + std::to_string(st[3]);
+        }
+        return {};
+    }
     bool pair_stats(int idx, dfb_tvl1_stats *out) override {
         *out = dfb_tvl1_stats{};
         if (idx < 0 || idx >= pair_log_count_ || idx < pair_log_count_ - kPairLog) return false;
@@ -566,7 +581,7 @@ class Tvl1 final : public FlowAlgorithm {
         }
         batch.jobs = job_ring_d_[jr];
         batch.host_jobs = host_jobs;
-        launches += launch_tvl1_fused(batch, device_, s);
+        launches += launch_tvl1_fused(batch, device_, s, prm_.serial_launches != 0);
         if (prm_.time_kernels) {
             DFB_CUDA(cudaEventRecord(timing_ev_[timing_used_][1], s));
             ++timing_used_;

@@ -46,6 +46,7 @@ namespace {
 #endif
 constexpr int kThreads = DFB_FUSED_THREADS;
 constexpr int kWarps = kThreads / 32;
+constexpr int kPartialSet = 256;  // stride between the two sets of per-CTA convergence partials (>= CTAs per lane)
 #ifndef DFB_FUSED_RPT
 #define DFB_FUSED_RPT 4
 #endif
@@ -83,15 +84,33 @@ __device__ __forceinline__ unsigned long long gtime() {
 // (G = CTAs in the lane's group).
 // bar.sync orders the CTA's writes before thread 0's gpu-scope fence + atomic (release); the
 // fence after the spin makes other CTAs' writes visible and invalidates this SM's L1.
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch, int G) {
+__device__ __noinline__ void barrier_stalled(FusedHostCtl *ctl, unsigned epoch, unsigned v, int G) {
+    volatile unsigned *st = ctl->stall;
+    st[1] = blockIdx.x;
+    st[2] = epoch;
+    st[3] = v;
+    st[4] = (unsigned)G;
+    st[5] = blockIdx.x / (unsigned)G;
+    __threadfence_system();
+    st[0] = 1;
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch, int G, FusedHostCtl *ctl) {
     __syncthreads();
     if (threadIdx.x == 0) {
         epoch += G;
         __threadfence();
         atomicAdd(counter, 1u);
-        unsigned v;
+        unsigned v, polls = 0;
+        unsigned long long t0 = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if ((++polls & 0xffffu) == 0) {  // ~every 30 ms of polling: the watchdog costs nothing on the normal path
+                const unsigned long long now = gtime();
+                if (!t0) t0 = now;
+                else if (now - t0 > kFusedStallNs) barrier_stalled(ctl, epoch, v, G);
+            }
         } while ((int)(v - epoch) < 0);
         __threadfence();
     }
@@ -577,6 +596,10 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
     int cur = 0;
     unsigned long long px_iters = 0, px_chunks = 0;
     int tile_base = 1;  // progress-counter epoch of the tile loop (sm.prog starts at 0)
+    // convergence partials are double-buffered: a CTA that leaves the barrier early may already write the NEXT check's partial
+    // while a slower one still sums this check's (at the small levels a 2-iteration chunk is a few microseconds); a divergent
+    // sum would desynchronise the barrier counts.  One barrier of lead is the most any CTA can have, so two sets suffice.
+    int part_sel = 0;
     unsigned tma_parity = 0;
     Prof prof;
     prof.init(sm.prof, bid == 0);
@@ -592,13 +615,13 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
         cur = 0;  // level start: u[0] holds the upsampled (or zero) flow, p[0] is zeroed
         phase_level_start(G, bid, job, L, s == job.nscales - 1);
         prof.mark(0);
-        grid_barrier(bar, epoch, G);
+        grid_barrier(bar, epoch, G, job.ctl);
         prof.mark(3);
         const double scaled_eps = job.epsilon * job.epsilon * (double)((long long)L.w * L.h);  // A.4
         for (int wi = 0; wi < job.warps; ++wi) {
             phase_warp(G, bid, job, L, cur);
             prof.mark(1);
-            grid_barrier(bar, epoch, G);
+            grid_barrier(bar, epoch, G, job.ctl);
             prof.mark(3);
             double error = DBL_MAX, prev_error = 0.0;
             int n = 0;
@@ -649,13 +672,13 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                                 bs += sm.red[k];
                                 sm.red[k] = 0.0;
                             }
-                            job.partials[bid] = bs;
+                            job.partials[part_sel * kPartialSet + bid] = bs;
                         }
                     }
                     prof.mark(2, 8 + s);
                     if (prof.on) prof.acc[16 + s] += 1;
                     px_chunks += (unsigned long long)(L.w * L.h);
-                    grid_barrier(bar, epoch, G);
+                    grid_barrier(bar, epoch, G, job.ctl);
                     prof.mark(3);
                     cur ^= 1;
                     remaining -= kk;
@@ -665,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                     // every CTA sums all partials in the same fixed order -> identical decisions everywhere
                     if (threadIdx.x < 32) {
                         double v = 0.0;
-                        for (int i = threadIdx.x; i < G; i += 32) v += __ldcg(job.partials + i);
+                        for (int i = threadIdx.x; i < G; i += 32) v += __ldcg(job.partials + part_sel * kPartialSet + i);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                         if (threadIdx.x == 0) sm.bcast[0] = v;
@@ -673,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
                     __syncthreads();
                     error = sm.bcast[0];
                     __syncthreads();
+                    part_sel ^= 1;
                     prev_error = error;
                 } else {
                     error = DBL_MAX;
@@ -685,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, kFusedCtasPerSm) k_tvl1_pair(const _
         if (s > 0) {
             phase_upsample(G, bid, job, L, job.lv[s - 1], cur);
             prof.mark(4);
-            grid_barrier(bar, epoch, G);
+            grid_barrier(bar, epoch, G, job.ctl);
             prof.mark(3);
         }
     }
@@ -735,7 +759,7 @@ static void configure_kernel() {
                                  std::to_string(kFusedCtasPerSm));
 }
 
-int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
+int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s, bool serialise) {
     // the opt-in shared-memory size is a per-device function attribute: handles on several devices may live in one process
     static std::mutex mtx;
     static bool configured[64] = {};
@@ -761,14 +785,29 @@ int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s) {
     attrs[0].val.cooperative = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    if (batch.njobs <= kFusedParamLanes) {
-        FusedBatchParams pb;
-        pb.njobs = batch.njobs;
-        pb.group = batch.group;
-        std::memcpy(pb.job, batch.host_jobs, sizeof(FusedJob) * batch.njobs);
-        DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatchParams>, pb));
-    } else {
-        DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatch>, batch));
+    // Persistent kernels with grid-wide barriers must never be PARTIALLY resident.  The cooperative launch checks the grid
+    // against an empty device only: two such grids launched from different streams (two handles on one GPU, e.g. two list
+    // workers) can each be given some of the SMs and then wait for the rest forever — seen with 128-CTA grids, where the
+    // second grid fits beside the first.  Launches of this kernel on one device are therefore chained through an event so
+    // that they execute one after another.
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        const int d = device >= 0 && device < 64 ? device : 0;
+        static cudaEvent_t last_done[64] = {};
+        if (serialise) {
+            if (!last_done[d]) DFB_CUDA(cudaEventCreateWithFlags(&last_done[d], cudaEventDisableTiming));
+            else DFB_CUDA(cudaStreamWaitEvent(s, last_done[d], 0));
+        }
+        if (batch.njobs <= kFusedParamLanes) {
+            FusedBatchParams pb;
+            pb.njobs = batch.njobs;
+            pb.group = batch.group;
+            std::memcpy(pb.job, batch.host_jobs, sizeof(FusedJob) * batch.njobs);
+            DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatchParams>, pb));
+        } else {
+            DFB_CUDA(cudaLaunchKernelEx(&cfg, k_tvl1_pair<FusedBatch>, batch));
+        }
+        if (serialise) DFB_CUDA(cudaEventRecord(last_done[d], s));
     }
     return 1;
 }

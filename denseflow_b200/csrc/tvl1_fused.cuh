@@ -24,7 +24,11 @@ struct FusedHostCtl {
     // CTA-0 view of where the last pair's time went, in ns (globaltimer): [0] level start, [1] warps,
     // [2] tile compute, [3] grid barriers, [4] upsample+merge, [8+s] tile compute at scale s, [16+s] chunks at scale s
     unsigned long long prof[32];
+    // watchdog of the grid barrier: a CTA that polls longer than kFusedStallNs records {1, blockIdx.x, barrier target,
+    // counter value, CTAs per lane, lane} here and traps, so a lost arrival surfaces as a CUDA error instead of a hung device
+    unsigned stall[8];
 };
+constexpr unsigned long long kFusedStallNs = 20ull * 1000 * 1000 * 1000;
 
 struct FusedJob {
     int nscales, warps, iterations, k;
@@ -93,6 +97,6 @@ inline int fused_cta_slots(int device) { return fused_num_sms(device) * kFusedCt
 // plane: base pointer, extent w x h (elements / rows), row pitch in elements.
 void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pitch);
 // returns the number of kernels launched
-int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s);
+int launch_tvl1_fused(const FusedBatch &batch, int device, cudaStream_t s, bool serialise);
 
 }  // namespace dfb
