@@ -38,7 +38,7 @@ struct Tvl1Params {
     int use_tma = 1;
     int prefetch = 1;
     int lanes = 0;  // pairs solved side by side per fused launch; 0 = choose from the tile counts
-    int serial_launches = 1;  // fused launches of all handles on one device execute one after another (event chain)
+    int serial_launches = 0;  // 1: fused launches of all handles on one device execute strictly one after another (event chain)
 };
 
 class Tvl1 final : public FlowAlgorithm {

@@ -64,7 +64,8 @@ const char *dfb_last_error(const dfb_handle *h);
  * visit, default 8), "lanes" (pairs solved side by side per launch, 0 = auto [default], up to 64), "flag_sync" (1 =
  * neighbour-warp progress flags in the tile loop [default], 0 = CTA-wide barriers), "use_tma" (1 = TMA staging of the
  * shared-memory tiles [default]), "prefetch" (1 = L2 prefetch of a CTA's next tile during the iterations [default]),
- * "time_kernels" (CUDA-event timing of the dominant kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma"
+ * "serial_launches" (1 = the fused launches of all handles on one device run strictly one after another; 0 [default] = a
+ * second handle's launch fills the SMs the first one's finished lanes free), "time_kernels" (CUDA-event timing of the dominant kernel, see dfb_counters).  farn: "num_levels" "num_iters" "poly_sigma"
  * (winSize 13, polyN 5, pyrScale 0.5 are fixed), "use_tma" (1 = persistent TMA-staged iteration kernel [default], 0 = the
  * LDG-staged one), "time_kernels".  Every combination of the engine knobs produces bit-identical flows.
  */

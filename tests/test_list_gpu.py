@@ -65,3 +65,29 @@ def test_list_float_flows_and_negative_step():
         for j in range(want.shape[0]):
             assert np.array_equal(got[(i, j)], want[j]), (i, j)
     assert st["flows"] == sum(max(len(c) - 2, 0) for c in clips)
+
+
+@pytest.mark.parametrize("serial", ["0", "1"])
+def test_two_workers_on_one_gpu_many_lanes(serial, monkeypatch):
+    """BASELINE.json configs[4] shape (340x256x64) with two workers on ONE device: 36-lane launches of the two handles
+    overlap (serial_launches 0) or are chained (1); every flow equals the single-handle result.  Regression test for the
+    convergence-partial race that desynchronised the lane barrier under exactly this load."""
+    import denseflow_b200 as d
+    monkeypatch.setenv("DFB_TVL1_SERIAL_LAUNCHES", serial)
+    base = [list(synth.stream(256, 340, 64, seed=900 + i, phase=2.0 * i)) for i in range(2)]
+    clips = [base[i % 2] for i in range(16)]
+    e = d.create("tvl1", 0, 340, 256)
+    assert e.get("serial_launches") == float(serial)
+    want = [e.calc_batch(c, step=1, bound=32) for c in base]
+    bad = []
+    lock = threading.Lock()
+
+    def on_chunk(clip, dev, first, last, qx, qy, flows):
+        w = want[clip % 2]
+        for k in range(len(qx)):
+            if not (np.array_equal(qx[k], w[0][first + k]) and np.array_equal(qy[k], w[1][first + k])):
+                with lock:
+                    bad.append((clip, first + k))
+
+    st = listrun.run_list("tvl1", [0, 0], clips, step=1, bound=32, on_chunk=on_chunk)
+    assert st["flows"] == 16 * 63 and not bad, bad[:5]
