@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tvl1_1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=16, help="frame pairs per step")
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step (default 16; 63 = one 64-frame clip for the 340x256 / 256x256 workloads)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=3, help="pairs timed for cpu_baseline (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     # BASELINE.json configs[4]: a fixed list of clips dispatched over the GPUs from one dynamic queue (strong scaling)
@@ -77,7 +77,10 @@ def parse():
     # the reference's per-batch chain minus decode / file IO: BGR frames -> gray -> resize -> flow -> quantise -> 2 JPEGs per pair
     ap.add_argument("--chain", action="store_true", help="chain mode: dfb_process_bgr_batch_host on BGR frames of --chain-src size")
     ap.add_argument("--chain-src", default="", help="WxH of the decoded BGR frames (default: the workload's size, i.e. no resize)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.pairs <= 0:
+        args.pairs = 63 if args.workload in ("tvl1_340x256", "tvl1_256") else 16
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -721,6 +724,7 @@ def main():
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    shard.barrier()  # rank 0's parity check runs after the last timing collective: every rank leaves together
     eng.release()
     try:
         import torch.distributed as dist

@@ -50,6 +50,9 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const void *tmap, int x, int 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // generic-proxy accesses to shared memory before this fence are ordered before later async-proxy (TMA) writes to it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global memory written through the generic proxy (plain stores, by this or — after a barrier this thread has observed — by
+// other CTAs) is ordered before the async-proxy (TMA) reads this thread issues afterwards
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 #endif
 
 }  // namespace dfb

@@ -422,6 +422,9 @@ __device__ __forceinline__ float process_tile(const FusedJob &job, const Tvl1Con
         __syncthreads();
         if (threadIdx.x == 0) {
             const char *maps = static_cast<const char *>(job.tmaps) + (size_t)level * kFusedMapsPerLevel * kTensorMapBytes;
+            // the planes were written with plain stores by other CTAs of the lane (previous chunk / warp phase) and published by
+            // the grid barrier this thread polled: order those generic-proxy writes before the async-proxy reads below
+            fence_proxy_async_global();
             mbar_expect_tx(&sm.tma_bar, 6u * kConstPlane * (unsigned)sizeof(float));
             tma_load_2d(sm.consts[0], maps + 0 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
             tma_load_2d(sm.consts[1], maps + 1 * kTensorMapBytes, rx0, ry0, &sm.tma_bar);
