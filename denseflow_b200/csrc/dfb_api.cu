@@ -39,8 +39,7 @@ struct dfb_handle {
     uint8_t *h_frame[kFrameRing] = {};
     float *h_flow[kFlowRing] = {};
     uint8_t *h_q[kFlowRing] = {};
-    // resize coefficient tables on the device, rebuilt when the geometry changes
-    std::unique_ptr<JpegEncoder> jpeg;  // created on first use
+    std::unique_ptr<JpegEncoder> jpeg;  // nvJPEG encoder / decoder states, created on first use
     // scratch of dfb_process_bgr_batch_host (grown on demand)
     cudaStream_t s_fetch = nullptr;       // bitstream read-back of the BGR chain
     std::vector<cudaEvent_t> pb_events;   // events of the BGR chain (grown on demand)
@@ -49,7 +48,7 @@ struct dfb_handle {
     uint8_t *dec_bgr = nullptr;  // BGR scratch of dfb_decode_jpeg_gray_device
     size_t dec_bgr_cap = 0;
     void *png_scratch = nullptr;  // min/max partials + ticket + bounds of dfb_flow_to_png_image_device
-    ResizeTap *d_taps = nullptr;
+    ResizeTap *d_taps = nullptr;  // resize coefficient tables on the device, rebuilt when the geometry changes
     int taps_cap = 0, taps_sw = 0, taps_sh = 0, taps_dw = 0, taps_dh = 0;
 };
 
@@ -664,6 +663,12 @@ int dfb_process_bgr_batch_host(dfb_handle *h, const uint8_t *const *bgr, int n_f
     const int M = std::max(n_frames - astep, 0);
     if (M == 0) return DFB_OK;
     if (!jpg_x || !jpg_y || !len_x || !len_y) return fail(h, DFB_ERR_INVALID_ARG, "null output");
+    for (int f = 0; f < n_frames; ++f)
+        if (!bgr[f] || host_pointer_kind(bgr[f]) < 0)
+            return fail(h, DFB_ERR_INVALID_ARG, "bgr[" + std::to_string(f) + "] is null or a device pointer (host entry point)");
+    for (int j = 0; j < M; ++j)
+        if (!jpg_x[j] || !jpg_y[j] || host_pointer_kind(jpg_x[j]) < 0 || host_pointer_kind(jpg_y[j]) < 0)
+            return fail(h, DFB_ERR_INVALID_ARG, "jpeg output " + std::to_string(j) + " is null or a device pointer (host entry point)");
     return guarded(h, [&]() {
         DFB_CUDA(cudaSetDevice(h->device));
         ensure_host_path(h);

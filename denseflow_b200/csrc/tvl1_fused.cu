@@ -745,8 +745,10 @@ void fused_encode_tensor_map(void *out, const float *plane, int w, int h, int pi
 }
 
 int fused_num_sms(int device) {
+    static std::mutex m;
     static int num_sms[64] = {};
     if (device < 0 || device >= 64) return 148;
+    std::lock_guard<std::mutex> lk(m);  // handles are created and used from several host threads (list workers)
     if (num_sms[device] == 0) DFB_CUDA(cudaDeviceGetAttribute(&num_sms[device], cudaDevAttrMultiProcessorCount, device));
     return num_sms[device];
 }

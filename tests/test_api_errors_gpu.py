@@ -52,6 +52,26 @@ def test_device_pointers_are_rejected_by_the_host_entry_points():
     assert L.dfb_calc_batch_host(e._h, fp, 2, 1, 128, 96, op) == _lib.DFB_ERR_INVALID_ARG
 
 
+def test_bgr_chain_rejects_null_and_device_pointers():
+    import torch
+    import denseflow_b200 as d
+    e = d.OpticalFlowDual_TVL1.create(0, 128, 96)
+    L = _lib.load()
+    host = np.zeros((96, 128, 3), np.uint8)
+    dev = torch.zeros((96, 128, 3), dtype=torch.uint8, device="cuda")
+    cap = L.dfb_jpeg_max_bytes(128, 96)
+    jx, jy = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    lx, ly = (C.c_size_t * 1)(), (C.c_size_t * 1)()
+    xp, yp = (C.c_void_p * 1)(jx.ctypes.data), (C.c_void_p * 1)(jy.ctypes.data)
+    for bad in ((C.c_void_p * 2)(host.ctypes.data, dev.data_ptr()), (C.c_void_p * 2)(host.ctypes.data, None)):
+        assert L.dfb_process_bgr_batch_host(e._h, bad, 2, 1, 128, 96, 0, 0, 20, 95, xp, yp, cap, lx, ly) == _lib.DFB_ERR_INVALID_ARG
+        assert b"bgr[1]" in L.dfb_last_error(e._h)
+    fp = (C.c_void_p * 2)(host.ctypes.data, host.ctypes.data)
+    assert L.dfb_process_bgr_batch_host(e._h, fp, 2, 1, 128, 96, 0, 0, 20, 95, (C.c_void_p * 1)(None), yp, cap, lx, ly) == _lib.DFB_ERR_INVALID_ARG
+    assert L.dfb_process_bgr_batch_host(e._h, fp, 2, 1, 128, 96, 0, 0, 20, 95, xp, yp, cap, lx, ly) == _lib.DFB_OK
+    assert lx[0] > 100 and ly[0] > 100
+
+
 def test_pitch_and_alignment_checks_on_device_entry_points():
     import torch
     import denseflow_b200 as d
