@@ -103,14 +103,10 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch,
         __threadfence();
         atomicAdd(counter, 1u);
         unsigned v, polls = 0;
-        unsigned long long t0 = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if ((++polls & 0xffffu) == 0) {  // ~every 30 ms of polling: the watchdog costs nothing on the normal path
-                const unsigned long long now = gtime();
-                if (!t0) t0 = now;
-                else if (now - t0 > kFusedStallNs) barrier_stalled(ctl, epoch, v, G);
-            }
+            // watchdog: counts polls, not wall time — a context that is switched out (time-sliced GPU) does not age
+            if (++polls == kFusedStallPolls) barrier_stalled(ctl, epoch, v, G);
         } while ((int)(v - epoch) < 0);
         __threadfence();
     }

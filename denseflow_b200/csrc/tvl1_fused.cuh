@@ -24,11 +24,12 @@ struct FusedHostCtl {
     // CTA-0 view of where the last pair's time went, in ns (globaltimer): [0] level start, [1] warps,
     // [2] tile compute, [3] grid barriers, [4] upsample+merge, [8+s] tile compute at scale s, [16+s] chunks at scale s
     unsigned long long prof[32];
-    // watchdog of the grid barrier: a CTA that polls longer than kFusedStallNs records {1, blockIdx.x, barrier target,
-    // counter value, CTAs per lane, lane} here and traps, so a lost arrival surfaces as a CUDA error instead of a hung device
+    // watchdog of the grid barrier: a CTA that polls the arrival counter kFusedStallPolls times (an L2 round trip each: 10-25 s)
+    // records {1, blockIdx.x, barrier target, counter value, CTAs per lane, lane} here and traps, so a lost arrival surfaces
+    // as a CUDA error instead of a hung device
     unsigned stall[8];
 };
-constexpr unsigned long long kFusedStallNs = 20ull * 1000 * 1000 * 1000;
+constexpr unsigned kFusedStallPolls = 1u << 25;
 
 struct FusedJob {
     int nscales, warps, iterations, k;
