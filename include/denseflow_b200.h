@@ -30,7 +30,8 @@ enum {
     DFB_OK = 0,
     DFB_ERR_INVALID_ARG = -1,
     DFB_ERR_UNKNOWN_ALGORITHM = -2, /* reference: std::runtime_error("unknown optical algorithm ...") src/denseflow_gpu.cpp:336 */
-    DFB_ERR_CUDA = -3,
+    DFB_ERR_CUDA = -3,              /* a CUDA call failed; the message carries the runtime's text and, when the tvl1 kernel's grid-barrier
+                                       watchdog fired, "[k_tvl1_pair grid-barrier watchdog: CTA .. lane ..]".  The context is unusable after it */
     DFB_ERR_SIZE = -4,              /* frame larger than max_width x max_height given at create, or a/b mismatch */
     DFB_ERR_UNSUPPORTED = -5,       /* "nv" / "brox": outside this build (reference: "not enabled, pls recompile" :296) */
     DFB_ERR_NO_DEVICE = -6
